@@ -1,0 +1,114 @@
+// kmx_internal.h -- declarations shared by the .cu files of libkmx_sm100 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace kmx {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+
+// ---- stage 1 (s1_superk.cu) -------------------------------------------------------------
+struct S1Args {
+  const uint8_t* text;          // text base
+  u64 text_bytes;
+  const u32* seg_start;         // per segment: offset in text
+  const u32* seg_len;           // per segment: number of bases
+  u64 nseg;
+  int k, m, wlen;               // wlen = k - m + 1
+  int max_nk;                   // max k-mers per record
+  u32 P;
+  const uint16_t* repart;       // [4^m]
+  void* records;                // bucket slab (uint4 units)
+  const u64* boff;              // [P] record offset of each partition's region
+  const u32* bcap;              // [P] capacity (records)
+  u32* cursor;                  // [P] records appended (may exceed bcap -> overflow)
+  u64* kcnt;                    // [P] k-mers appended
+  u32* overflow;                // set when a record did not fit
+  u32 stage_cap;                // staging capacity (records)
+  u32 flush_thr;                // flush when staged > flush_thr
+};
+size_t s1_smem_bytes(int W, u32 stage_cap, int wlen, u32 P);
+u64 fq_num_tiles(const uint8_t* text, u64 nbytes);
+cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
+                            u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,
+                            int phase, cudaStream_t st, u64* launches);
+cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches);
+
+// ---- stage 2 (s2_count.cu) --------------------------------------------------------------
+struct S2Common {
+  int W;                  // words per k-mer (1 or 2)
+  int k;
+  u32 P;
+  const void* records;    // bucket slab
+  const u64* boff;        // [P] device
+  const u32* bcnt;        // [P] device: records per partition
+  u32 max_bcnt;           // host copy of max(bcnt)
+};
+
+// hash mode, histogram path
+static const u32 HIST_SUB = 65536;   // slots per sub-chunk
+cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi,
+                             u32* hist /* P*Wbits */, u32 hard_min, u32* sub_counts /* P*S */, u32 S,
+                             cudaStream_t st, u64* launches);
+cudaError_t launch_hash_emit(u32 P, u64 Wbits, u32 S, u32* hist, u32 hard_min, const u64* sub_off,
+                             u64* out_keys, u32* out_counts, cudaStream_t st, u64* launches);
+cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
+
+// generic path: expand -> keys, segmented radix sort, run-length
+cudaError_t launch_expand_keys(const S2Common& c, int key_kind, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi,
+                               const u64* koff /* [P] device: key offset of partition */,
+                               u32* kcursor /* [P] device, zeroed */, u64* keys_lo, u64* keys_hi,
+                               cudaStream_t st, u64* launches);
+
+struct SegSortPlan;   // opaque, built on host
+// Segmented LSD radix sort (8-bit digits) of nseg segments of 64/128-bit keys with optional
+// 64-bit payload.  Segment i = [seg_off[i], seg_off[i+1]).  Buffers are ping-ponged; returns
+// (via *result_in_alt) whether the sorted data ended in the alt buffers.
+cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off /* host [nseg+1] */,
+                                 u64* lo, u64* hi /* may be NULL */, u64* pay /* may be NULL */,
+                                 u64* lo_alt, u64* hi_alt, u64* pay_alt,
+                                 int begin_bit, int end_bit /* key bits [begin,end) */,
+                                 void* d_work, size_t work_bytes, size_t* work_needed,
+                                 int* result_in_alt, cudaStream_t st, u64* launches);
+
+// run-length + hard-min over sorted segments.
+// phase 0: counts survivors per tile -> tile_counts ; phase 1: writes (key,count) at tile_off.
+cudaError_t launch_rle(int phase, u32 ntiles, const u64* d_tile_seg_begin, const u64* d_tile_seg_end,
+                       const u64* d_tile_begin, const u64* d_tile_end,
+                       const u64* lo, const u64* hi, u32 hard_min,
+                       u32* tile_counts, const u64* tile_off,
+                       u64* out_lo, u64* out_hi, u32* out_counts, cudaStream_t st, u64* launches);
+
+// ---- stage 3/4 (s3_merge.cu) ------------------------------------------------------------
+struct MergeList { const u64* lo; const u64* hi; const u32* cnt; u64 n; };
+// dense (hash bf/bft) path: rows addressed by key - lower
+cudaError_t launch_dense_solid(const MergeList* d_lists, u32 N, const u32* d_soft, u64 lower, u32* solid_in,
+                               u64 max_n, cudaStream_t st, u64* launches);
+cudaError_t launch_dense_emit(const MergeList* d_lists, u32 N, const u32* d_soft, u32 rmin, u32 share,
+                              u64 lower, const u32* solid_in /* may be NULL when not needed */,
+                              uint8_t* slab, u32 row_bytes, u64* stats /* 6N */, u64 max_n,
+                              cudaStream_t st, u64* launches);
+// sparse path (count / pa rows): entries sorted by key with payload (sample<<32 | count)
+cudaError_t launch_sparse_heads(const u64* lo, const u64* hi, u64 n, u32* head_flag, cudaStream_t st, u64* launches);
+cudaError_t launch_sparse_rows(int phase, const u64* lo, const u64* hi, const u64* pay, u64 n,
+                               const u64* row_of /* inclusive scan of heads - 1 */, const u32* d_soft,
+                               u32 rmin, u32 share, u32 emit_all, u32* solid_in, u32* keep_flag,
+                               const u64* out_row /* exclusive scan of keep */, u32 N, int W, int fmt,
+                               uint8_t* body, u32 row_bytes, uint8_t* row_keep, u64* stats,
+                               cudaStream_t st, u64* launches);
+cudaError_t launch_scan_flags(const u32* flags, u64* out_excl, u64 n, u64* total, void* work, cudaStream_t st, u64* launches);
+size_t scan_flags_work_bytes(u64 n);
+cudaError_t launch_row_keep(const u32* solid_in, u64 nrows, u32 rmin, u32 emit_all, u32* keep_flag, cudaStream_t st, u64* launches);
+
+// ---- stage 4 (s4_bits.cu) ---------------------------------------------------------------
+cudaError_t launch_transpose_bits(const uint8_t* in, u64 nrows, u64 ncols, uint8_t* out, cudaStream_t st, u64* launches);
+cudaError_t launch_hash_vector(const u64* keys, u64 n, u64 lower, uint8_t* bits, cudaStream_t st, u64* launches);
+
+// ---- synth (synth.cu) -------------------------------------------------------------------
+cudaError_t launch_synth_fastq(u64 seed, u32 sample, u64 first_read, u64 R, u32 L, u64 G, u32 thr_d, u32 thr_e,
+                               int revcomp, char* out, cudaStream_t st, u64* launches);
+
+}  // namespace kmx

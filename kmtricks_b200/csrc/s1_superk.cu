@@ -1,0 +1,418 @@
+// s1_superk.cu -- stage 1: FASTQ text -> 2-bit encode -> minimizer -> repartition scatter.
+//
+// Replaces (behaviour, not code) gatb Model::iterate / ModelMinimizer (Model.hpp:725-765,
+// 1040-1139,1220-1287), Sequence2SuperKmer (Sequence2SuperKmer.hpp:90-158) and
+// KmFillPartitions::processSuperkmer (include/kmtricks/gatb/fill_partitions.hpp:59-105).
+//
+// Kernels:
+//   fq_count_newlines / fq_index_lines : strict 4-line FASTQ line index (sequence start/len
+//       per record) built on the device with 128-bit loads, ballot-free popcount of '\n'.
+//   s1_superk<W> : one thread per sequence segment streams its bases, keeps the rolling
+//       forward / reverse-complement m-mer, computes lut(m-mer) arithmetically (canonical
+//       m-mer + "AA" ban) instead of gathering an 8 MiB table, and maintains the sliding
+//       minimum over the k-m+1 m-mers with a divergence-free block prefix/suffix-min ring
+//       in shared memory.  A super-k-mer record is cut when the minimizer changes, the
+//       k-mer is invalid, or the record is full.  Records are staged per CTA in shared
+//       memory and flushed with ONE global atomic per (CTA flush, partition) into the
+//       per-partition bucket slabs in HBM (128-bit stores).
+#include "common.cuh"
+#include "kmx_internal.h"
+
+namespace kmx {
+
+// ------------------------------------------------------------------------------------
+// FASTQ line index
+// ------------------------------------------------------------------------------------
+static constexpr int FQ_THREADS = 256;
+static constexpr int FQ_BYTES_PER_THREAD = 64;                 // 4 x uint4
+static constexpr int FQ_TILE = FQ_THREADS * FQ_BYTES_PER_THREAD;
+
+__device__ __forceinline__ u32 count_nl_u32(u32 v)
+{
+  // bytes equal to 0x0A -> count
+  u32 x = v ^ 0x0A0A0A0Au;                          // zero byte <=> '\n'
+  u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;   // high bit set iff byte != 0 (exact, no borrow)
+  return __popc(~y & 0x80808080u);
+}
+
+// `base` is the 16B-aligned address at or below the text start, `lead` = text - base.
+__global__ void __launch_bounds__(FQ_THREADS)
+fq_count_newlines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total /* lead + n */,
+                  u32* __restrict__ tile_counts)
+{
+  __shared__ u32 s_sum[FQ_THREADS / 32];
+  u64 tile0 = (u64)blockIdx.x * FQ_TILE;
+  u32 cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    u64 off = tile0 + ((u64)j * FQ_THREADS + threadIdx.x) * 16;
+    if (off < nbytes_total) {
+      uint4 v = __ldg(base + off / 16);
+      u32 wv[4] = {v.x, v.y, v.z, v.w};
+      if (off >= lead && off + 16 <= nbytes_total) {
+        cnt += count_nl_u32(wv[0]) + count_nl_u32(wv[1]) + count_nl_u32(wv[2]) + count_nl_u32(wv[3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+          u64 pos = off + b;
+          u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+          if (pos >= lead && pos < nbytes_total && c == 0x0Au) cnt++;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0;
+    for (int i = 0; i < FQ_THREADS / 32; i++) t += s_sum[i];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+// single-CTA exclusive scan of tile counts (u32 -> u64 prefix); also total
+__global__ void __launch_bounds__(1024) scan_u32_to_u64(const u32* __restrict__ in, u64* __restrict__ out, u64 n, u64* total)
+{
+  __shared__ u64 s_warp[32];
+  __shared__ u64 s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (u64 base = 0; base < n; base += 1024) {
+    u64 i = base + threadIdx.x;
+    u64 v = (i < n) ? in[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      u64 w = s_warp[threadIdx.x], xw = w;
+      for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= o) xw += y; }
+      s_warp[threadIdx.x] = xw - w;
+    }
+    __syncthreads();
+    u64 carry = s_carry;
+    u64 excl = carry + s_warp[threadIdx.x >> 5] + x - v;
+    if (i < n) out[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = s_carry;
+}
+
+// For newline number g (0-based) at text position pos:
+//   g%4==0 -> sequence of record g/4 starts at pos+1 ; g%4==1 -> it ends at pos (exclusive)
+//   g%4==3 -> next char must be '@' (or end) ; g%4==1 -> next char must be '+'
+__global__ void __launch_bounds__(FQ_THREADS)
+fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
+               const u64* __restrict__ tile_prefix, u32* __restrict__ seq_start,
+               u32* __restrict__ seq_len, u64 nrec, u32* __restrict__ flags /* [0]=format error, [1]=max len */)
+{
+  __shared__ u32 s_warp[FQ_THREADS / 32];
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
+  u64 tile0 = (u64)blockIdx.x * FQ_TILE;
+  // each thread owns 64 contiguous bytes here (blocked, so newline order == thread order)
+  u64 off = tile0 + (u64)threadIdx.x * FQ_BYTES_PER_THREAD;
+  u32 wv[16];
+  u32 cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    u64 o = off + j * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (o < nbytes_total) v = __ldg(base + o / 16);
+    wv[4 * j] = v.x; wv[4 * j + 1] = v.y; wv[4 * j + 2] = v.z; wv[4 * j + 3] = v.w;
+  }
+#pragma unroll
+  for (int b = 0; b < 64; b++) {
+    u64 pos = off + b;
+    u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+    if (pos >= lead && pos < nbytes_total && c == 0x0Au) cnt++;
+  }
+  u32 x = cnt;
+  for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  u32 wbase = 0;
+  for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s_warp[i];
+  u64 g = tile_prefix[blockIdx.x] + wbase + x - cnt;
+  if (cnt == 0) return;
+#pragma unroll 1
+  for (int b = 0; b < 64; b++) {
+    u64 pos = off + b;
+    u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+    if (pos >= lead && pos < nbytes_total && c == 0x0Au) {
+      u64 rec = g >> 2; u32 ph = (u32)(g & 3);
+      u64 tpos = pos - lead;                       // position relative to text start
+      if (rec < nrec) {
+        if (ph == 0) seq_start[rec] = (u32)(tpos + 1);
+        else if (ph == 1) {
+          seq_len[rec] = (u32)tpos;                // end (exclusive); fixed up to a length later
+          if (pos + 1 < nbytes_total && bytes[pos + 1] != '+') atomicOr(&flags[0], 1u);
+        } else if (ph == 3) {
+          if (pos + 1 < nbytes_total && bytes[pos + 1] != '@') atomicOr(&flags[0], 1u);
+        }
+      }
+      g++;
+    }
+  }
+}
+
+// seq_len[r] currently holds the end offset; turn into a length, strip one trailing '\r'
+// (kseq drops it when the line is longer than 1, BankFasta.cpp:476-477), track max length.
+__global__ void fq_fix_len(const uint8_t* __restrict__ text, const u32* __restrict__ seq_start,
+                           u32* __restrict__ seq_len, u64 nrec, u32* __restrict__ flags)
+{
+  u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u32 len = 0;
+  if (r < nrec) {
+    u32 s = seq_start[r], e = seq_len[r];
+    if (e < s) { atomicOr(&flags[0], 1u); e = s; }
+    len = e - s;
+    if (len > 1 && text[e - 1] == '\r') len--;
+    seq_len[r] = len;
+    if (r == 0 && text[0] != '@') atomicOr(&flags[0], 1u);
+  }
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0 && len) atomicMax(&flags[1], len);
+}
+
+// ------------------------------------------------------------------------------------
+// main stage-1 kernel
+// ------------------------------------------------------------------------------------
+template <int W> struct RecT;
+template <> struct RecT<1> { typedef uint4 type; };
+template <> struct RecT<2> { struct __align__(16) type { uint4 a, b; }; };
+
+
+
+static constexpr int S1_THREADS = 128;
+static constexpr int S1_ROUND = 8;
+
+template <int W>
+__global__ void __launch_bounds__(S1_THREADS)
+s1_superk(const S1Args a)
+{
+  typedef typename RecT<W>::type Rec;
+  extern __shared__ __align__(16) unsigned char smem[];
+  // layout: recs[stage_cap] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | part[stage_cap] | rank[stage_cap]
+  Rec* s_rec = reinterpret_cast<Rec*>(smem);
+  u32* s_ring = reinterpret_cast<u32*>(s_rec + a.stage_cap);
+  u32* s_hist = s_ring + a.wlen * S1_THREADS;
+  u32* s_gbase = s_hist + a.P;
+  u32* s_kc = s_gbase + a.P;
+  uint16_t* s_part = reinterpret_cast<uint16_t*>(s_kc + a.P);
+  uint16_t* s_rank = s_part + a.stage_cap;
+  __shared__ u32 s_count;
+  __shared__ u32 s_maxlen;
+
+  const int tid = threadIdx.x;
+  const int k = a.k, m = a.m, wlen = a.wlen;
+  const u32 mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+  const u32 ban_mask = 0x55555555u & ((1u << (2 * (m - 2))) - 1u);
+  const int rsh = 2 * (m - 1);
+
+  for (u32 p = tid; p < a.P; p += S1_THREADS) { s_hist[p] = 0; s_kc[p] = 0; }
+  for (int j = 0; j < wlen; j++) s_ring[j * S1_THREADS + tid] = 0xFFFFFFFFu;
+  if (tid == 0) { s_count = 0; s_maxlen = 0; }
+  __syncthreads();
+
+  u64 seg = (u64)blockIdx.x * S1_THREADS + tid;
+  u32 len = 0; u64 start = 0;
+  if (seg < a.nseg) { len = a.seg_len[seg]; start = a.seg_start[seg]; }
+  if (len < (u32)k) len = 0;                    // Sequence2SuperKmer.hpp:143-144
+  {
+    u32 ml = len;
+    for (int o = 16; o > 0; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+    if ((tid & 31) == 0) atomicMax(&s_maxlen, ml);
+  }
+  __syncthreads();
+  const u32 maxlen = s_maxlen;
+
+  // char reader: aligned 8-byte words
+  const uint8_t* addr = a.text + start;
+  const u64* wp = reinterpret_cast<const u64*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)7);
+  int bi = (int)(reinterpret_cast<uintptr_t>(addr) & 7);
+  const u64* wend = reinterpret_cast<const u64*>((reinterpret_cast<uintptr_t>(a.text) + a.text_bytes + 7) & ~(uintptr_t)7);
+  u64 wcur = (len && wp < wend) ? __ldg(wp) : 0;
+
+  u32 fm = 0, rm = 0;                 // rolling forward / revcomp m-mer
+  u64 acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // shift register of recent bases (acc0 lowest)
+  int bad = 0;                        // >0 : k-mer ending here is invalid
+  u32 nk = 0;                         // k-mers in the open record
+  u32 cur_min = 0, cur_p = 0;
+  u32 pre = 0xFFFFFFFFu;
+  int j = 0;                          // m-mer index mod wlen (uniform)
+
+  auto flush_record = [&]() {
+    // open record holds the last n = k + nk - 1 bases of acc
+    u32 n = (u32)k + nk - 1;
+    u32 slot = atomicAdd(&s_count, 1u);
+    if (W == 1) {
+      u64 lo = acc0, hi = acc1;
+      if (n < 32) { lo &= ((1ULL << (2 * n)) - 1ULL); hi = 0; }
+      else if (n < 64) { hi &= ((1ULL << (2 * (n - 32))) - 1ULL); }
+      hi |= (u64)n << 56;
+      uint4 r; r.x = (u32)lo; r.y = (u32)(lo >> 32); r.z = (u32)hi; r.w = (u32)(hi >> 32);
+      reinterpret_cast<uint4*>(s_rec)[slot] = r;
+    } else {
+      u64 v0 = acc0, v1 = acc1, v2 = acc2, v3 = acc3;
+      // mask to 2n bits, n <= 124
+      u32 bits = 2 * n;
+      if (bits < 64) { v0 &= ((1ULL << bits) - 1ULL); v1 = v2 = v3 = 0; }
+      else if (bits < 128) { if (bits > 64) v1 &= ((1ULL << (bits - 64)) - 1ULL); else v1 = 0; v2 = v3 = 0; }
+      else if (bits < 192) { if (bits > 128) v2 &= ((1ULL << (bits - 128)) - 1ULL); else v2 = 0; v3 = 0; }
+      else { if (bits > 192) v3 &= ((1ULL << (bits - 192)) - 1ULL); else v3 = 0; }
+      v3 |= (u64)n << 56;
+      uint4* dst = reinterpret_cast<uint4*>(s_rec) + 2 * slot;
+      uint4 r0, r1;
+      r0.x = (u32)v0; r0.y = (u32)(v0 >> 32); r0.z = (u32)v1; r0.w = (u32)(v1 >> 32);
+      r1.x = (u32)v2; r1.y = (u32)(v2 >> 32); r1.z = (u32)v3; r1.w = (u32)(v3 >> 32);
+      dst[0] = r0; dst[1] = r1;
+    }
+    s_part[slot] = (uint16_t)cur_p;
+    s_rank[slot] = (uint16_t)nk;          // nk parked here until the flush computes ranks
+    nk = 0;
+  };
+
+  for (u32 i0 = 0; i0 < maxlen; i0 += S1_ROUND) {
+#pragma unroll 1
+    for (u32 ii = 0; ii < S1_ROUND; ii++) {
+      const u32 i = i0 + ii;
+      const bool active = i < len;
+      u32 c = 0; bool valid = false;
+      if (active) {
+        u32 ch = (u32)(wcur >> (8 * bi)) & 0xFFu;
+        if (++bi == 8) { bi = 0; ++wp; wcur = (wp < wend) ? __ldg(wp) : 0; }
+        c = nt_code(ch); valid = nt_valid(ch);
+      }
+      fm = ((fm << 2) | c) & mmask;
+      rm = (rm >> 2) | ((c ^ 2u) << rsh);
+      bad = valid ? max(bad - 1, 0) : k;
+      u32 wmin = 0xFFFFFFFFu;
+      if (i + 1 >= (u32)m) {                           // uniform
+        u32 canon = min(fm, rm);
+        u32 t = ~(canon | (canon >> 2));
+        t = ((t >> 1) & t) & ban_mask;
+        u32 lutv = t ? mmask : canon;
+        u32 s = (j + 1 < wlen) ? s_ring[(j + 1) * S1_THREADS + tid] : 0xFFFFFFFFu;
+        s_ring[j * S1_THREADS + tid] = lutv;
+        pre = (j == 0) ? lutv : min(pre, lutv);
+        wmin = min(s, pre);
+        if (++j == wlen) {
+          j = 0;
+          u32 accm = 0xFFFFFFFFu;
+          for (int t2 = wlen - 1; t2 >= 0; t2--) {
+            accm = min(accm, s_ring[t2 * S1_THREADS + tid]);
+            s_ring[t2 * S1_THREADS + tid] = accm;
+          }
+        }
+      }
+      if (active) {
+        const bool kvalid = (i + 1 >= (u32)k) && (bad == 0);
+        if (nk && (!kvalid || wmin != cur_min || nk == (u32)a.max_nk)) flush_record();
+        // shift the base in
+        if (W == 2) { acc3 = (acc3 << 2) | (acc2 >> 62); acc2 = (acc2 << 2) | (acc1 >> 62); }
+        acc1 = (acc1 << 2) | (acc0 >> 62);
+        acc0 = (acc0 << 2) | c;
+        if (kvalid) {
+          if (nk == 0) { cur_min = wmin; cur_p = __ldg(a.repart + wmin); }
+          nk++;
+        }
+        if (i + 1 == len && nk) flush_record();
+      }
+    }
+    __syncthreads();
+    if (s_count > a.flush_thr || i0 + S1_ROUND >= maxlen) {
+      const u32 n = s_count;
+      for (u32 r = tid; r < n; r += S1_THREADS) {
+        u32 p = s_part[r];
+        u32 nkr = s_rank[r];
+        s_rank[r] = (uint16_t)atomicAdd(&s_hist[p], 1u);
+        atomicAdd(&s_kc[p], nkr);
+      }
+      __syncthreads();
+      for (u32 p = tid; p < a.P; p += S1_THREADS) {
+        u32 cnt = s_hist[p];
+        if (cnt) {
+          s_gbase[p] = atomicAdd(&a.cursor[p], cnt);
+          atomicAdd(&a.kcnt[p], (u64)s_kc[p]);
+          s_hist[p] = 0; s_kc[p] = 0;
+        }
+      }
+      __syncthreads();
+      Rec* out = reinterpret_cast<Rec*>(a.records);
+      for (u32 r = tid; r < n; r += S1_THREADS) {
+        u32 p = s_part[r];
+        u32 pos = s_gbase[p] + s_rank[r];
+        if (pos < a.bcap[p]) out[a.boff[p] + pos] = s_rec[r];
+        else *a.overflow = 1u;
+      }
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host-side launchers (called from kmx_api.cu)
+// ------------------------------------------------------------------------------------
+size_t s1_smem_bytes(int W, u32 stage_cap, int wlen, u32 P)
+{
+  size_t rec = (W == 1) ? 16 : 32;
+  return (size_t)stage_cap * rec + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)stage_cap * 4;
+}
+
+cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
+                            u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,
+                            int phase, cudaStream_t st, u64* launches)
+{
+  uintptr_t ta = reinterpret_cast<uintptr_t>(text);
+  const uint4* base = reinterpret_cast<const uint4*>(ta & ~(uintptr_t)15);
+  u64 lead = ta & 15, tot = lead + nbytes;
+  u64 ntiles = (tot + FQ_TILE - 1) / FQ_TILE;
+  if (phase == 0) {
+    fq_count_newlines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_counts);
+    scan_u32_to_u64<<<1, 1024, 0, st>>>(tile_counts, tile_prefix, ntiles, d_total);
+    *launches += 2;
+  } else {
+    fq_index_lines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_prefix, seq_start, seq_len, nrec_cap, flags);
+    fq_fix_len<<<(unsigned)((nrec_cap + 255) / 256), 256, 0, st>>>(text, seq_start, seq_len, nrec_cap, flags);
+    *launches += 2;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches)
+{
+  scan_u32_to_u64<<<1, 1024, 0, st>>>(in, out, n, total);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+u64 fq_num_tiles(const uint8_t* text, u64 nbytes)
+{
+  u64 lead = reinterpret_cast<uintptr_t>(text) & 15;
+  return (lead + nbytes + FQ_TILE - 1) / FQ_TILE;
+}
+
+cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches)
+{
+  if (a.nseg == 0) return cudaSuccess;
+  size_t smem = s1_smem_bytes(W, a.stage_cap, a.wlen, a.P);
+  unsigned grid = (unsigned)((a.nseg + S1_THREADS - 1) / S1_THREADS);
+  cudaError_t e;
+  if (W == 1) {
+    e = cudaFuncSetAttribute(s1_superk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    s1_superk<1><<<grid, S1_THREADS, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(s1_superk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    s1_superk<2><<<grid, S1_THREADS, smem, st>>>(a);
+  }
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace kmx

@@ -1,0 +1,217 @@
+// s2_hash.cu -- stage 2, hash keys, histogram path.
+//
+// Replaces (behaviour, not code) ReadSuperkHash / HashSort / HashPartCounter::executeDump
+// (include/kmtricks/gatb/sorting_count.hpp:387-470,525-528,971-990), KmXXHash (:346-363) and
+// HashCountProcessor (include/kmtricks/gatb/count_processor.hpp:61-70).
+//
+// The reference sorts all hashes of a (sample, partition) and run-length counts them.  Hash
+// keys live in a dense window [W*p, W*(p+1)), so here each super-k-mer record is expanded in
+// registers (every k-mer extracted independently from the packed record, canonical via
+// bit-reversal, XXH64, exact multiply-shift modulo) and counted with one L2 atomic into a
+// W-slot u32 histogram of the partition.  The add that lifts a slot to `hard_min` also bumps
+// the survivor counter of the slot's 64K sub-chunk, so a single ordered sweep (hash_emit) can
+// compact the survivors into the ascending (key,count) list and zero the histogram again.
+#include "common.cuh"
+#include "kmx_internal.h"
+
+namespace kmx {
+
+// extract the k-mer starting at base j of a w=1 record (n bases, V big-endian in 120 bits)
+__device__ __forceinline__ u64 rec1_kmer(u64 lo, u64 hi, int n, int k, int j)
+{
+  int sh = 2 * (n - k - j);                 // right shift of the 128-bit value
+  u64 v;
+  if (sh == 0) v = lo;
+  else if (sh < 64) v = (lo >> sh) | (hi << (64 - sh));
+  else v = hi >> (sh - 64);
+  return (k == 32) ? v : (v & ((1ULL << (2 * k)) - 1ULL));
+}
+
+// 256-bit right shift by sh (< 256), return low 128 bits
+__device__ __forceinline__ void shr256_lo128(u64 v0, u64 v1, u64 v2, u64 v3, int sh, u64& lo, u64& hi)
+{
+  int ws = sh >> 6, bs = sh & 63;
+  u64 a[6] = {v0, v1, v2, v3, 0, 0};
+  u64 x0 = a[ws], x1 = a[ws + 1], x2 = a[ws + 2];
+  if (bs == 0) { lo = x0; hi = x1; }
+  else { lo = (x0 >> bs) | (x1 << (64 - bs)); hi = (x1 >> bs) | (x2 << (64 - bs)); }
+}
+
+__device__ __forceinline__ void rec2_kmer(u64 v0, u64 v1, u64 v2, u64 v3, int n, int k, int j, u64& lo, u64& hi)
+{
+  // select by branches instead of a dynamically indexed local array
+  int sh = 2 * (n - k - j);
+  int ws = sh >> 6, bs = sh & 63;
+  u64 x0, x1, x2;
+  if (ws == 0) { x0 = v0; x1 = v1; x2 = v2; }
+  else if (ws == 1) { x0 = v1; x1 = v2; x2 = v3; }
+  else if (ws == 2) { x0 = v2; x1 = v3; x2 = 0; }
+  else { x0 = v3; x1 = 0; x2 = 0; }
+  if (bs == 0) { lo = x0; hi = x1; }
+  else { lo = (x0 >> bs) | (x1 << (64 - bs)); hi = (x1 >> bs) | (x2 << (64 - bs)); }
+  int hb = 2 * (k - 32);                    // k > 32 here
+  if (hb < 64) hi &= ((1ULL << hb) - 1ULL);
+}
+
+// canonical k-mer of record k-mer j: min(fwd, revcomp)
+template <int W>
+__device__ __forceinline__ void record_canon(const uint4* __restrict__ recs, u64 ridx, int k, int j, u64& clo, u64& chi);
+
+struct Rec1 { u64 lo, hi; int n; };
+struct Rec2 { u64 v0, v1, v2, v3; int n; };
+
+__device__ __forceinline__ Rec1 load_rec1(const uint4* __restrict__ recs, u64 ridx)
+{
+  uint4 r = __ldg(recs + ridx);
+  Rec1 o;
+  o.lo = (u64)r.x | ((u64)r.y << 32);
+  u64 h = (u64)r.z | ((u64)r.w << 32);
+  o.n = (int)(h >> 56);
+  o.hi = h & 0x00FFFFFFFFFFFFFFULL;
+  return o;
+}
+__device__ __forceinline__ Rec2 load_rec2(const uint4* __restrict__ recs, u64 ridx)
+{
+  uint4 a = __ldg(recs + 2 * ridx), b = __ldg(recs + 2 * ridx + 1);
+  Rec2 o;
+  o.v0 = (u64)a.x | ((u64)a.y << 32); o.v1 = (u64)a.z | ((u64)a.w << 32);
+  o.v2 = (u64)b.x | ((u64)b.y << 32);
+  u64 h = (u64)b.z | ((u64)b.w << 32);
+  o.n = (int)(h >> 56);
+  o.v3 = h & 0x00FFFFFFFFFFFFFFULL;
+  return o;
+}
+
+__device__ __forceinline__ void canon1(const Rec1& r, int k, int j, u64& c)
+{
+  u64 f = rec1_kmer(r.lo, r.hi, r.n, k, j);
+  u64 rc = revcomp64(f, k);
+  c = f < rc ? f : rc;
+}
+__device__ __forceinline__ void canon2(const Rec2& r, int k, int j, u64& clo, u64& chi)
+{
+  u64 flo, fhi, rlo, rhi;
+  rec2_kmer(r.v0, r.v1, r.v2, r.v3, r.n, k, j, flo, fhi);
+  revcomp128(flo, fhi, k, rlo, rhi);
+  bool fl = (fhi < rhi) || (fhi == rhi && flo < rlo);
+  clo = fl ? flo : rlo; chi = fl ? fhi : rhi;
+}
+
+static constexpr int HH_THREADS = 256;
+
+// grid: (x tiles, P).  One thread per record, loop over its k-mers.
+template <int W>
+__global__ void __launch_bounds__(HH_THREADS)
+hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
+                 int k, u64 Wbits, FastMod64 fm, u32* __restrict__ hist, u32 hmin,
+                 u32* __restrict__ sub_counts, u32 S)
+{
+  const u32 p = blockIdx.y;
+  const u32 n = bcnt[p];
+  const u64 b0 = boff[p];
+  u32* __restrict__ h = hist + (u64)p * Wbits;
+  u32* __restrict__ sc = sub_counts + (u64)p * S;
+  for (u32 r = blockIdx.x * HH_THREADS + threadIdx.x; r < n; r += gridDim.x * HH_THREADS) {
+    if (W == 1) {
+      Rec1 rec = load_rec1(recs, b0 + r);
+      int nk = rec.n - k + 1;
+      for (int j = 0; j < nk; j++) {
+        u64 c; canon1(rec, k, j, c);
+        u64 key = fastmod64(xxh64_8(c), fm);
+        u32 old = atomicAdd(h + key, 1u);
+        if (old + 1u == hmin) atomicAdd(sc + (u32)(key / HIST_SUB), 1u);
+      }
+    } else {
+      Rec2 rec = load_rec2(recs, b0 + r);
+      int nk = rec.n - k + 1;
+      for (int j = 0; j < nk; j++) {
+        u64 clo, chi; canon2(rec, k, j, clo, chi);
+        u64 key = fastmod64(xxh64_16(clo, chi), fm);
+        u32 old = atomicAdd(h + key, 1u);
+        if (old + 1u == hmin) atomicAdd(sc + (u32)(key / HIST_SUB), 1u);
+      }
+    }
+  }
+}
+
+// grid = P*S CTAs; CTA (p, s) sweeps slots [s*HIST_SUB, min(W, (s+1)*HIST_SUB)) in order.
+static constexpr int HE_THREADS = 256;
+__global__ void __launch_bounds__(HE_THREADS)
+hash_emit_kernel(u64 Wbits, u32 S, u32* __restrict__ hist, u32 hmin, const u64* __restrict__ sub_off,
+                 u64* __restrict__ out_keys, u32* __restrict__ out_counts)
+{
+  __shared__ u32 s_warp[HE_THREADS / 32];
+  __shared__ u32 s_run;
+  const u32 p = blockIdx.x / S, s = blockIdx.x % S;
+  const u64 slot0 = (u64)s * HIST_SUB;
+  const u64 slot1 = min(Wbits, slot0 + HIST_SUB);
+  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)p * Wbits);   // W multiple of 64 -> aligned
+  const u64 key_base = (u64)p * Wbits;
+  u64 obase = sub_off[blockIdx.x];
+  if (sub_off[blockIdx.x + 1] == obase) {
+    // nothing survives here: still has to clear non-zero (below hard-min) slots
+    for (u64 q = slot0 / 4 + threadIdx.x; q < slot1 / 4; q += HE_THREADS) {
+      uint4 v = h4[q];
+      if (v.x | v.y | v.z | v.w) h4[q] = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (u64 q0 = slot0 / 4; q0 < slot1 / 4; q0 += HE_THREADS) {
+    u64 q = q0 + threadIdx.x;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q < slot1 / 4) {
+      v = h4[q];
+      if (v.x | v.y | v.z | v.w) h4[q] = make_uint4(0, 0, 0, 0);
+    }
+    u32 c = (v.x >= hmin) + (v.y >= hmin) + (v.z >= hmin) + (v.w >= hmin);
+    u32 x = c;
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    u32 wb = 0, tot = 0;
+    for (int i = 0; i < HE_THREADS / 32; i++) { u32 t = s_warp[i]; if (i < (int)(threadIdx.x >> 5)) wb += t; tot += t; }
+    u32 run = s_run;
+    u64 o = obase + run + wb + x - c;
+    if (c) {
+      u64 kb = key_base + q * 4;
+      if (v.x >= hmin) { out_keys[o] = kb; out_counts[o] = v.x; o++; }
+      if (v.y >= hmin) { out_keys[o] = kb + 1; out_counts[o] = v.y; o++; }
+      if (v.z >= hmin) { out_keys[o] = kb + 2; out_counts[o] = v.z; o++; }
+      if (v.w >= hmin) { out_keys[o] = kb + 3; out_counts[o] = v.w; o++; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = run + tot;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi,
+                             u32* hist, u32 hard_min, u32* sub_counts, u32 S,
+                             cudaStream_t st, u64* launches)
+{
+  if (c.max_bcnt == 0) return cudaSuccess;
+  FastMod64 fm; fm.d = mod_d; fm.mlo = mod_mlo; fm.mhi = mod_mhi;
+  unsigned gx = (c.max_bcnt + HH_THREADS - 1) / HH_THREADS;
+  if (gx > 4096) gx = 4096;
+  dim3 grid(gx, c.P);
+  u32 hmin = hard_min ? hard_min : 1;
+  if (c.W == 1)
+    hash_hist_kernel<1><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist, hmin, sub_counts, S);
+  else
+    hash_hist_kernel<2><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist, hmin, sub_counts, S);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hash_emit(u32 P, u64 Wbits, u32 S, u32* hist, u32 hard_min, const u64* sub_off,
+                             u64* out_keys, u32* out_counts, cudaStream_t st, u64* launches)
+{
+  u32 hmin = hard_min ? hard_min : 1;
+  hash_emit_kernel<<<P * S, HE_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_off, out_keys, out_counts);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace kmx

@@ -13,11 +13,21 @@
 using namespace kmx;
 
 namespace kmx {
+size_t scan_u32_work_bytes(u64 n);
+cudaError_t scan_u32_inplace(u32* d, u64 n, u32* d_total, void* work, cudaStream_t st, u64* launches);
+size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off);
+cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, u64* lo, u64* hi, u64* lo_alt, u64* hi_alt,
+                                 int W, int begin_bit, int end_bit, void* d_work, int* result_in_alt,
+                                 cudaStream_t st, u64* launches);
+size_t rle_work_bytes(u32 nseg, const u64* h_seg_off);
+cudaError_t rle_segments(u32 nseg, const u64* h_seg_off, const u64* lo, const u64* hi, int W, u32 hard_min,
+                         void* d_work, std::vector<u64>& h_tile_off, std::vector<u64>& h_seg_out_off,
+                         int phase, u64* out_lo, u64* out_hi, u32* out_cnt, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_solid(const MergeList* d_lists, u32 N, const u32* d_soft, const u64* ulo, const u64* uhi,
                                 u64 nu, int W, u32* solid_in, u64 max_n, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_emit(const MergeList* d_lists, u32 N, const u32* d_soft, u32 rmin, u32 share, u32 emit_all,
                                const u64* ulo, const u64* uhi, u64 nu, int W, const u32* solid_in,
-                               const u32* keep, const u64* out_row, int fmt, uint8_t* body, u32 row_bytes,
+                               const u32* keep, const u32* out_row, int fmt, uint8_t* body, u32 row_bytes,
                                uint8_t* row_keep, u64* stats, u64 max_n, cudaStream_t st, u64* launches);
 }
 

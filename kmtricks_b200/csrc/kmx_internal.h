@@ -63,25 +63,6 @@ cudaError_t launch_expand_keys(const S2Common& c, int key_kind, u64 Wbits, u64 m
                                u32* kcursor /* [P] device, zeroed */, u64* keys_lo, u64* keys_hi,
                                cudaStream_t st, u64* launches);
 
-struct SegSortPlan;   // opaque, built on host
-// Segmented LSD radix sort (8-bit digits) of nseg segments of 64/128-bit keys with optional
-// 64-bit payload.  Segment i = [seg_off[i], seg_off[i+1]).  Buffers are ping-ponged; returns
-// (via *result_in_alt) whether the sorted data ended in the alt buffers.
-cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off /* host [nseg+1] */,
-                                 u64* lo, u64* hi /* may be NULL */, u64* pay /* may be NULL */,
-                                 u64* lo_alt, u64* hi_alt, u64* pay_alt,
-                                 int begin_bit, int end_bit /* key bits [begin,end) */,
-                                 void* d_work, size_t work_bytes, size_t* work_needed,
-                                 int* result_in_alt, cudaStream_t st, u64* launches);
-
-// run-length + hard-min over sorted segments.
-// phase 0: counts survivors per tile -> tile_counts ; phase 1: writes (key,count) at tile_off.
-cudaError_t launch_rle(int phase, u32 ntiles, const u64* d_tile_seg_begin, const u64* d_tile_seg_end,
-                       const u64* d_tile_begin, const u64* d_tile_end,
-                       const u64* lo, const u64* hi, u32 hard_min,
-                       u32* tile_counts, const u64* tile_off,
-                       u64* out_lo, u64* out_hi, u32* out_counts, cudaStream_t st, u64* launches);
-
 // ---- stage 3/4 (s3_merge.cu) ------------------------------------------------------------
 struct MergeList { const u64* lo; const u64* hi; const u32* cnt; u64 n; };
 // dense (hash bf/bft) path: rows addressed by key - lower
@@ -91,16 +72,6 @@ cudaError_t launch_dense_emit(const MergeList* d_lists, u32 N, const u32* d_soft
                               u64 lower, const u32* solid_in /* may be NULL when not needed */,
                               uint8_t* slab, u32 row_bytes, u64* stats /* 6N */, u64 max_n,
                               cudaStream_t st, u64* launches);
-// sparse path (count / pa rows): entries sorted by key with payload (sample<<32 | count)
-cudaError_t launch_sparse_heads(const u64* lo, const u64* hi, u64 n, u32* head_flag, cudaStream_t st, u64* launches);
-cudaError_t launch_sparse_rows(int phase, const u64* lo, const u64* hi, const u64* pay, u64 n,
-                               const u64* row_of /* inclusive scan of heads - 1 */, const u32* d_soft,
-                               u32 rmin, u32 share, u32 emit_all, u32* solid_in, u32* keep_flag,
-                               const u64* out_row /* exclusive scan of keep */, u32 N, int W, int fmt,
-                               uint8_t* body, u32 row_bytes, uint8_t* row_keep, u64* stats,
-                               cudaStream_t st, u64* launches);
-cudaError_t launch_scan_flags(const u32* flags, u64* out_excl, u64 n, u64* total, void* work, cudaStream_t st, u64* launches);
-size_t scan_flags_work_bytes(u64 n);
 cudaError_t launch_row_keep(const u32* solid_in, u64 nrows, u32 rmin, u32 emit_all, u32* keep_flag, cudaStream_t st, u64* launches);
 
 // ---- stage 4 (s4_bits.cu) ---------------------------------------------------------------

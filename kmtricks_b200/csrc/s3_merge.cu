@@ -73,7 +73,7 @@ __global__ void row_keep_kernel(const u32* __restrict__ solid_in, u64 nrows, u32
 struct EmitArgs {
   const u32* soft; u32 rmin, share, emit_all;
   const u32* solid_in;       // NULL => not needed (share==0 && rmin<=1)
-  const u64* out_row;        // sparse: exclusive scan of keep flags (NULL for dense)
+  const u32* out_row;        // sparse: exclusive scan of keep flags (NULL for dense)
   const u32* keep;           // sparse: keep flag per row (NULL for dense)
   uint8_t* body; u32 row_bytes; u32 key_bytes; int fmt;
   uint8_t* row_keep;         // emit_all: default keep decision per emitted row
@@ -142,7 +142,7 @@ merge_emit_kernel(const MergeList* __restrict__ lists, Row rr, EmitArgs a)
 
 // sparse rows: write the key words of every kept row (+ default keep decision for emit_all)
 __global__ void sparse_keys_kernel(const u64* __restrict__ ulo, const u64* __restrict__ uhi, u64 nu, int W,
-                                   const u32* __restrict__ keep, const u64* __restrict__ out_row,
+                                   const u32* __restrict__ keep, const u32* __restrict__ out_row,
                                    const u32* __restrict__ solid_in, u32 rmin,
                                    uint8_t* __restrict__ body, u32 row_bytes, uint8_t* __restrict__ row_keep)
 {
@@ -216,7 +216,7 @@ cudaError_t launch_row_keep(const u32* solid_in, u64 nrows, u32 rmin, u32 emit_a
 
 cudaError_t launch_sparse_emit(const MergeList* d_lists, u32 N, const u32* d_soft, u32 rmin, u32 share, u32 emit_all,
                                const u64* ulo, const u64* uhi, u64 nu, int W, const u32* solid_in,
-                               const u32* keep, const u64* out_row, int fmt, uint8_t* body, u32 row_bytes,
+                               const u32* keep, const u32* out_row, int fmt, uint8_t* body, u32 row_bytes,
                                uint8_t* row_keep, u64* stats, u64 max_n, cudaStream_t st, u64* launches)
 {
   if (!nu) return cudaSuccess;

@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers/s of the repart->superk->count->merge hot path on synthetic FASTQ.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).
+A "step" is one pass of the whole hot path over one batch of synthetic input:
+  workload cfg2 (BASELINE.json configs[1]): S samples x R reads x 150 nt, k=31, hash:bf:bin,
+  P partitions, Bloom size B  ->  per-partition dense Bloom slabs (the .cmbf bodies).
+`value`  : k-mer occurrences / s with the FASTQ text already resident in HBM (device timing).
+`e2e`    : same metric through the host-buffer C-ABI path: FASTQ in pinned host memory,
+           H2D copies and the D2H read of every .cmbf body inside the timed region.
+`--impl reference` times the unmodified reference CPU pipeline (oracle/_ref/bin/kmtricks) on a
+bounded sample of the same workload with all host threads.
+Inputs are far larger than L2 (315 MB of text per sample launch vs 126 MB L2).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# survey §8(d) "Algorithmic bytes": S1 = read FASTQ + write buckets at the reference's compact
+# super-k-mer format (1.03 B per k-mer, measured on the reference's skp files)
+BUCKET_BYTES_PER_KMER = 1.03
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--genome", type=int, default=5_000_000)
+    ap.add_argument("--partitions", type=int, default=64)
+    ap.add_argument("--bloom-size", type=int, default=200_000_000)
+    ap.add_argument("--hard-min", type=int, default=2)
+    ap.add_argument("--kmer-size", type=int, default=31)
+    ap.add_argument("--mode", default="hash:bf:bin")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-samples", type=int, default=4, help="samples in the bounded CPU-reference run")
+    ap.add_argument("--ref-reads", type=int, default=250_000)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        self.mode = os.environ.get("KMX_BENCH_CLOCKS", "nvml")
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nv = pynvml
+                self.hd = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+                self.stop_flag = False
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.mode = "smi"
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        R = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+             "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        period = float(os.environ.get("KMX_BENCH_CLOCKS_MS", "200")) / 1e3
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.hd, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.hd, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.hd) / 1e3
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.hd)
+                self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if rs & v else "Not Active" for v in R.values()])
+            except Exception:
+                pass
+            time.sleep(period)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.mode == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=2)
+        elif not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.mode}
+
+
+def n_kmers(args):
+    return args.samples * args.reads * (args.read_len - args.kmer_size + 1)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference_once(args, workdir, threads):
+    """One bounded run of the unmodified reference pipeline; returns (seconds, kmers)."""
+    from oracle import oracle as O
+    fof = os.path.join(workdir, "fof.txt")
+    rd = os.path.join(workdir, "run")
+    shutil.rmtree(rd, ignore_errors=True)
+    kind, what = args.mode.split(":")[:2]
+    # same per-partition window as the full workload: bloom scaled to keep W
+    cmd = [O.REF_BIN, "pipeline", "--file", fof, "--run-dir", rd, "--kmer-size", str(args.kmer_size),
+           "--mode", f"{kind}:{what}:bin", "--hard-min", str(args.hard_min), "--nb-partitions", str(args.partitions),
+           "--minimizer-size", "10", "--static-repart", "--bloom-size", str(args.bloom_size), "-t", str(threads)]
+    t0 = time.perf_counter()
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    shutil.rmtree(rd, ignore_errors=True)
+    return dt, args.ref_samples * args.ref_reads * (args.read_len - args.kmer_size + 1)
+
+
+def make_ref_inputs(args, workdir):
+    from kmtricks_b200 import synth
+    with open(os.path.join(workdir, "fof.txt"), "w") as f:
+        for s in range(args.ref_samples):
+            p = os.path.join(workdir, f"S{s}.fastq")
+            with open(p, "wb") as g:
+                step = 50_000
+                for r0 in range(0, args.ref_reads, step):
+                    g.write(synth.make_fastq(1234, s, min(step, args.ref_reads - r0), L=args.read_len, G=args.genome,
+                                             d=2e-3, e=2e-3, revcomp=True, first_read=r0))
+            f.write(f"S{s}: {p}\n")
+
+
+def ref_workdir():
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return tempfile.mkdtemp(prefix="kmx_ref_", dir=base)
+
+
+def cpu_baseline(args):
+    from oracle import oracle as O
+    if not O.have_ref():
+        return {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/bin/kmtricks missing"}
+    wd = ref_workdir()
+    try:
+        make_ref_inputs(args, wd)
+        threads = os.cpu_count() or 1
+        dt, km = run_reference_once(args, wd, threads)
+        return {"value": km / dt, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                "sample": f"{args.ref_samples} samples x {args.ref_reads} reads x {args.read_len} nt of the same generator, "
+                          f"kmtricks pipeline --mode {args.mode} -t {threads} on {wd.split('/')[1]}, {dt:.2f} s wall incl. file I/O"}
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cfg = {"workload": f"cfg2-bounded: {args.ref_samples} samples x {args.ref_reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
+                       f"P={args.partitions}, bloom={args.bloom_size}, hard-min {args.hard_min} (bounded sample of {args.samples} x {args.reads})",
+           "l2": "inputs larger than L2"}
+    if not O.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/kmtricks not built (run oracle/build_ref.sh where /root/reference exists)"}))
+        return
+    wd = ref_workdir()
+    try:
+        make_ref_inputs(args, wd)
+        threads = os.cpu_count() or 1
+        for _ in range(args.warmup):
+            run_reference_once(args, wd, threads)
+        tot = 0.0; km = 0
+        for _ in range(args.steps):
+            dt, k1 = run_reference_once(args, wd, threads)
+            tot += dt; km += k1
+        val = km / tot
+        line = {"impl": "reference", "metric": "k-mers/s end-to-end (repart->merge)", "value": val, "unit": "k-mers/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": cfg,
+                "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                                 "sample": f"{args.ref_samples} x {args.ref_reads} reads per step, files on {wd.split('/')[1]}"},
+                "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+# --------------------------------------------------------------------------- kmx arm
+def main_kmx(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kmtricks_b200 import _lib, engine, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    # multi-GPU: samples shard over ranks (weak scaling: every rank parses `samples` samples)
+    cfg = engine.Config(kmer_size=args.kmer_size, nb_partitions=args.partitions, mode=args.mode, hard_min=args.hard_min,
+                        bloom_size=args.bloom_size)
+    N = args.samples
+    eng = engine.Engine(cfg, N, device=local)
+    L = eng.lib
+    h = eng.h
+    rb = synth.record_bytes(args.read_len)
+    sample_bytes = args.reads * rb
+    kmers_step = n_kmers(args)
+    P = args.partitions
+    Wb = cfg.window_bits
+    row_bytes = (N + 7) // 8
+    slab_bytes = Wb * row_bytes
+    fmt = cfg.fmt
+
+    def ck(rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: {L.kmx_last_error(h).decode()} ({rc})")
+
+    # ---- synthetic FASTQ resident in HBM (all samples)
+    d_text = C.c_void_p()
+    ck(L.kmx_dev_alloc(h, N * sample_bytes + 64, C.byref(d_text)), "dev_alloc text")
+    for s in range(N):
+        ck(L.kmx_synth_fastq(h, 1234, rank * N + s, 0, args.reads, args.read_len, args.genome, 2e-3, 2e-3, 1,
+                             d_text.value + s * sample_bytes), "synth")
+    ck(L.kmx_sync(h), "sync")
+    # all P bodies stay in HBM
+    d_out = C.c_void_p()
+    ck(L.kmx_dev_alloc(h, P * (slab_bytes + 64) if fmt in ("bf", "bft") else 64, C.byref(d_out)), "dev_alloc out")
+    soft = np.full(N, cfg.soft_min, dtype=np.uint32)
+    mp = _lib.KmxMergeParams(soft.ctypes.data_as(C.POINTER(C.c_uint32)), cfg.recurrence_min, cfg.share_min,
+                             {"count": 0, "pa": 1, "bf": 2, "bft": 3}[fmt], 0)
+    res = _lib.KmxMergeResult()
+
+    wall = {}
+
+    def tm(name, rc_fn, *a):
+        t0 = time.perf_counter()
+        rc = rc_fn(*a)
+        wall[name] = wall.get(name, 0.0) + time.perf_counter() - t0
+        ck(rc, name)
+
+    def step_device():
+        tm("reset", L.kmx_reset, h)
+        for s in range(N):
+            tm("begin", L.kmx_superk_begin, h)
+            tm("push", L.kmx_superk_push_fastq, h, d_text.value + s * sample_bytes, sample_bytes, 1)
+            tm("end", L.kmx_superk_end, h, None)
+            tm("count", L.kmx_count_sample, h, s, args.hard_min)
+        for p in range(P):
+            if fmt in ("bf", "bft"):
+                tm("set_out", L.kmx_set_merge_output, h, d_out.value + p * (slab_bytes + 64), slab_bytes + 64)
+            tm("merge", L.kmx_merge_partition, h, p, C.byref(mp), C.byref(res))
+        tm("set_out", L.kmx_set_merge_output, h, None, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ck(L.kmx_sync(h), "sync")
+
+    stream = torch.cuda.ExternalStream(L.kmx_stream(h), device=torch.device("cuda", local))
+
+    def timed(fn, steps):
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    ck(L.kmx_profile_enable(h, 1), "prof")
+    ck(L.kmx_profile_reset(h), "prof")
+    launches0 = L.kmx_launch_count(h)
+    wall.clear()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    host_wall = {k: round(1e3 * v / args.steps, 2) for k, v in wall.items()}
+    launches = (L.kmx_launch_count(h) - launches0) // max(args.steps, 1)
+    prof = {}
+    for i, name in enumerate(_lib.PROF_KINDS):
+        tms = C.c_double(); cnt = C.c_uint64()
+        ck(L.kmx_profile_get(h, i, C.byref(tms), C.byref(cnt)), "prof_get")
+        if cnt.value:
+            prof[name] = {"ms_per_step": tms.value / args.steps, "launches_per_step": cnt.value // args.steps}
+    ck(L.kmx_profile_enable(h, 0), "prof")
+    ms_step = ms / args.steps
+    value = world * kmers_step / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (device time share from the event spans)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kern_time = {k: v["ms_per_step"] for k, v in prof.items() if k not in ("fill",)}
+    top = max(kern_time, key=kern_time.get) if kern_time else None
+    roof = None
+    if top:
+        n_l = prof[top]["launches_per_step"]
+        dur_ms = prof[top]["ms_per_step"] / n_l
+        kmers_launch = kmers_step / N
+        if top == "s1_superk":
+            alg = sample_bytes + BUCKET_BYTES_PER_KMER * kmers_launch
+            what = "S1: FASTQ text read + super-k-mer buckets written (1.03 B/k-mer)"
+        elif top in ("hash_hist", "expand", "radix_sort", "rle", "hash_emit"):
+            alg = BUCKET_BYTES_PER_KMER * kmers_launch
+            what = "S2: buckets read (1.03 B/k-mer) [+12 B per surviving (key,sample)]"
+        else:
+            alg = slab_bytes
+            what = "S3/S4: slab written"
+        ach = alg / (dur_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": alg, "launch_ms": dur_ms, "what": what, "peak_source": peak_src}
+
+    # ---- end to end through host buffers (pinned FASTQ in, bodies out)
+    e2e = None
+    if not args.no_e2e:
+        h_text = C.c_void_p(); h_out = C.c_void_p()
+        rc = L.kmx_host_alloc(N * sample_bytes, C.byref(h_text))
+        rc2 = L.kmx_host_alloc(max(P * slab_bytes, 64), C.byref(h_out))
+        if rc or rc2:
+            e2e = {"value": None, "unit": "k-mers/s", "error": "pinned host allocation failed"}
+        else:
+            ck(L.kmx_memcpy_d2h(h, h_text, d_text, N * sample_bytes), "d2h text")
+            d2h = 0
+
+            def step_host():
+                ck(L.kmx_reset(h), "reset")
+                for s in range(N):
+                    ck(L.kmx_superk_begin(h), "begin")
+                    ck(L.kmx_superk_push_fastq(h, h_text.value + s * sample_bytes, sample_bytes, 0), "push")
+                    ck(L.kmx_superk_end(h, None), "end")
+                    ck(L.kmx_count_sample(h, s, args.hard_min), "count")
+                for p in range(P):
+                    ck(L.kmx_merge_partition(h, p, C.byref(mp), C.byref(res)), "merge")
+                    ck(L.kmx_merge_get(h, h_out.value + p * slab_bytes, None, None), "merge_get")
+
+            step_host()
+            t0 = time.perf_counter()
+            ms_e = timed(step_host, max(1, min(args.steps, 2)))
+            wall = time.perf_counter() - t0
+            ns = max(1, min(args.steps, 2))
+            e2e = {"value": world * kmers_step / (ms_e / ns * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": N * sample_bytes,
+                   "d2h_bytes_per_step": P * slab_bytes, "ms_per_step": ms_e / ns, "wall_s_per_step": wall / ns}
+            L.kmx_host_free(h_text); L.kmx_host_free(h_out)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {"metric": "k-mers/s end-to-end (repart->merge)", "value": value, "unit": "k-mers/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": f"cfg2: {N} samples x {args.reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
+                                       f"P={P}, bloom={args.bloom_size}, hard-min {args.hard_min}, --static-repart, m=10"
+                                       + (f"; per GPU, {world} GPUs" if world > 1 else ""),
+                           "kmers_per_step": kmers_step, "l2": "inputs larger than L2 (315 MB text per launch)",
+                           "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in prof.items()},
+                "host_wall_ms_per_step": host_wall, "device_bytes": int(L.kmx_device_bytes(h))}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_kmx(a)

@@ -139,6 +139,16 @@ int kmx_memcpy_h2d(kmx_ctx* ctx, void* dev, const void* host, size_t nbytes);
 /* pinned host memory for the end-to-end path */
 int kmx_host_alloc(size_t nbytes, void** host_ptr);
 int kmx_host_free(void* host_ptr);
+/* the next KMX_FMT_BF / KMX_FMT_BFT merges write their body to this device buffer (>= body
+ * bytes + 8) instead of the context's own; NULL restores the default                         */
+int kmx_set_merge_output(kmx_ctx* ctx, void* dev_ptr, size_t cap_bytes);
+/* per-kernel-class device timing with CUDA events on the context's stream (bench roofline) */
+enum { KMX_PROF_INDEX = 0, KMX_PROF_S1 = 1, KMX_PROF_HASH_HIST = 2, KMX_PROF_HASH_EMIT = 3, KMX_PROF_EXPAND = 4,
+       KMX_PROF_SORT = 5, KMX_PROF_RLE = 6, KMX_PROF_MERGE = 7, KMX_PROF_TRANSPOSE = 8, KMX_PROF_FILL = 9,
+       KMX_PROF_KINDS = 10 };
+int kmx_profile_enable(kmx_ctx* ctx, int on);
+int kmx_profile_reset(kmx_ctx* ctx);
+int kmx_profile_get(kmx_ctx* ctx, int kind, double* total_ms, uint64_t* count);
 /* drops all per-sample lists and buckets (keeps parameters) */
 int kmx_reset(kmx_ctx* ctx);
 /* bytes of device memory currently held by the context */

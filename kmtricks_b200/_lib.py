@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libkmx_sm100.so")
 KMX_OK, KMX_ERR_ARG, KMX_ERR_CUDA, KMX_ERR_FORMAT, KMX_ERR_NOMEM, KMX_ERR_STATE = range(6)
 KEY_KMER, KEY_HASH = 0, 1
 FMT_COUNT, FMT_PA, FMT_BF, FMT_BFT = 0, 1, 2, 3
+PROF_KINDS = ["fq_index", "s1_superk", "hash_hist", "hash_emit", "expand", "radix_sort", "rle", "merge", "transpose", "fill"]
 
 
 class KmxParams(C.Structure):
@@ -58,6 +59,10 @@ SYMBOLS = {
     "kmx_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "kmx_host_free": (_i, [_vp]),
     "kmx_reset": (_i, [_vp]),
+    "kmx_set_merge_output": (_i, [_vp, _vp, _sz]),
+    "kmx_profile_enable": (_i, [_vp, _i]),
+    "kmx_profile_reset": (_i, [_vp]),
+    "kmx_profile_get": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "kmx_device_bytes": (_u64, [_vp]),
 }
 

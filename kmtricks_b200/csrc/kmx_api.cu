@@ -43,6 +43,8 @@ struct ListRef {            // one (sample, partition) list in HBM
 
 struct ArenaBlock { char* p; size_t cap, used; };
 
+struct ProfSpan { cudaEvent_t a, b; int kind; };
+
 }  // namespace
 
 struct kmx_ctx {
@@ -55,6 +57,12 @@ struct kmx_ctx {
   u64 launches = 0;
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
+  bool prof_on = false;
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[KMX_PROF_KINDS] = {0};
+  u64 prof_cnt[KMX_PROF_KINDS] = {0};
+  void* merge_out = nullptr; size_t merge_out_cap = 0;
 
   uint16_t* d_repart = nullptr;
   // ---- stage 1
@@ -86,6 +94,31 @@ static int fail(kmx_ctx* c, int code, const char* fmt, ...)
   if (c) c->err = buf;
   return code;
 }
+static cudaEvent_t prof_event(kmx_ctx* c)
+{
+  cudaEvent_t e;
+  if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  kmx_ctx* c; ProfSpan s; bool on;
+  ProfScope(kmx_ctx* c_, int kind) : c(c_), on(c_->prof_on) { if (on) { s.kind = kind; s.a = prof_event(c); s.b = prof_event(c); cudaEventRecord(s.a, c->st); } }
+  ~ProfScope() { if (on) { cudaEventRecord(s.b, c->st); c->prof_spans.push_back(s); } }
+};
+#define PROF(kind) ProfScope prof_scope_##kind(ctx, kind)
+static void prof_collect(kmx_ctx* c)
+{
+  if (c->prof_spans.empty()) return;
+  cudaStreamSynchronize(c->st);
+  for (auto& s : c->prof_spans) {
+    float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
+    c->prof_ms[s.kind] += ms; c->prof_cnt[s.kind] += 1;
+    c->prof_pool.push_back(s.a); c->prof_pool.push_back(s.b);
+  }
+  c->prof_spans.clear();
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMX_ERR_NOMEM : KMX_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 static cudaError_t ensure(kmx_ctx* ctx, DBuf& b, size_t bytes, bool keep = false)
@@ -206,7 +239,7 @@ extern "C" int kmx_reset(kmx_ctx* ctx)
 {
   if (!ctx) return KMX_ERR_ARG;
   CK(cudaStreamSynchronize(ctx->st));
-  arena_clear(ctx);
+  for (auto& b : ctx->arena) b.used = 0;          // keep the blocks: no cudaFree/cudaMalloc per step
   for (auto& l : ctx->lists) l = ListRef();
   ctx->in_sample = ctx->sample_ready = false;
   return KMX_OK;
@@ -289,7 +322,7 @@ static int run_s1(kmx_ctx* ctx, const uint8_t* d_text, u64 text_bytes, const u32
     a.P = P; a.repart = ctx->d_repart; a.records = ctx->records.p; a.boff = ctx->d_boff; a.bcap = ctx->d_bcap;
     a.cursor = ctx->d_cursor; a.kcnt = ctx->d_kcnt; a.overflow = ctx->d_flags + 2;
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
-    CK(launch_s1(ctx->W, a, ctx->st, &ctx->launches));
+    { PROF(KMX_PROF_S1); CK(launch_s1(ctx->W, a, ctx->st, &ctx->launches)); }
     std::vector<u32> cur(P); std::vector<u64> kc(P); u32 ovf = 0;
     CK(cudaMemcpyAsync(cur.data(), ctx->d_cursor, P * 4, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(kc.data(), ctx->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -318,7 +351,7 @@ extern "C" int kmx_superk_push_fastq(kmx_ctx* ctx, const char* text, size_t nbyt
   const u64 ntiles = fq_num_tiles(d_text, nbytes);
   CK(ensure(ctx, ctx->tile_counts, ntiles * 4));
   CK(ensure(ctx, ctx->tile_prefix, ntiles * 8));
-  CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total, nullptr, nullptr, 0, nullptr, 0, ctx->st, &ctx->launches));
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total, nullptr, nullptr, 0, nullptr, 0, ctx->st, &ctx->launches)); }
   u64 nl = 0; uint8_t last = 0;
   CK(cudaMemcpyAsync(&nl, ctx->d_total, 8, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaMemcpyAsync(&last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->st));
@@ -330,8 +363,8 @@ extern "C" int kmx_superk_push_fastq(kmx_ctx* ctx, const char* text, size_t nbyt
   CK(ensure(ctx, ctx->seq_start, nrec * 4));
   CK(ensure(ctx, ctx->seq_len, nrec * 4));
   CK(cudaMemsetAsync(ctx->d_flags, 0, 8, ctx->st));
-  CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total,
-                     (u32*)ctx->seq_start.p, (u32*)ctx->seq_len.p, nrec, ctx->d_flags, 1, ctx->st, &ctx->launches));
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total,
+                     (u32*)ctx->seq_start.p, (u32*)ctx->seq_len.p, nrec, ctx->d_flags, 1, ctx->st, &ctx->launches)); }
   u32 fl[2] = {0, 0};
   CK(cudaMemcpyAsync(fl, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
@@ -411,7 +444,7 @@ static int count_hash_hist(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
   S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ctx->records.p; c.boff = ctx->d_boff;
   c.bcnt = ctx->d_cursor; c.max_bcnt = *std::max_element(ctx->h_cursor.begin(), ctx->h_cursor.end());
   u64 mlo, mhi; fastmod_magic(Wb, mlo, mhi);
-  CK(launch_hash_hist(c, Wb, Wb, mlo, mhi, (u32*)ctx->hist.p, hard_min, (u32*)ctx->sub_counts.p, S, ctx->st, &ctx->launches));
+  { PROF(KMX_PROF_HASH_HIST); CK(launch_hash_hist(c, Wb, Wb, mlo, mhi, (u32*)ctx->hist.p, hard_min, (u32*)ctx->sub_counts.p, S, ctx->st, &ctx->launches)); }
   u64* so = (u64*)ctx->sub_off.p;
   CK(launch_scan_u32((const u32*)ctx->sub_counts.p, so, (u64)P * S, so + (u64)P * S, ctx->st, &ctx->launches));
   std::vector<u64> h_so((size_t)P * S + 1);
@@ -421,7 +454,7 @@ static int count_hash_hist(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
   void* kp = nullptr; void* cp = nullptr;
   CK(arena_alloc(ctx, D * 8, &kp));
   CK(arena_alloc(ctx, D * 4, &cp));
-  CK(launch_hash_emit(P, Wb, S, (u32*)ctx->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ctx->st, &ctx->launches));
+  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ctx->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ctx->st, &ctx->launches)); }
   for (u32 p = 0; p < P; p++) {
     ListRef& L = ctx->lists[(size_t)sample * P + p];
     u64 b = h_so[(size_t)p * S], e = h_so[(size_t)(p + 1) * S];
@@ -544,25 +577,35 @@ extern "C" int kmx_merge_partition(kmx_ctx* ctx, uint32_t partition, const kmx_m
   const u64 Wb = ctx->prm.window_bits;
   const u32 rb = (N + 7) / 8;
   const size_t slab_bytes = (size_t)Wb * rb;
-  CK(ensure(ctx, ctx->body, slab_bytes + 8));
-  CK(cudaMemsetAsync(ctx->body.p, 0, slab_bytes + 8, ctx->st));
+  uint8_t* slab = nullptr;
+  if (ctx->merge_out && mp->format == KMX_FMT_BF) {
+    if (ctx->merge_out_cap < slab_bytes + 8) return fail(ctx, KMX_ERR_ARG, "merge output buffer too small (%zu < %zu)", ctx->merge_out_cap, slab_bytes + 8);
+    slab = (uint8_t*)ctx->merge_out;
+  } else { CK(ensure(ctx, ctx->body, slab_bytes + 8)); slab = (uint8_t*)ctx->body.p; }
+  { PROF(KMX_PROF_FILL); CK(cudaMemsetAsync(slab, 0, slab_bytes + 8, ctx->st)); }
   const bool need_si = mp->share_min != 0 || mp->recurrence_min > 1;
   u32* si = nullptr;
   if (need_si) {
     CK(ensure(ctx, ctx->solid_in, Wb * 4));
     CK(cudaMemsetAsync(ctx->solid_in.p, 0, Wb * 4, ctx->st));
     si = (u32*)ctx->solid_in.p;
-    CK(launch_dense_solid((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, Wb * partition, si, max_n, ctx->st, &ctx->launches));
+    { PROF(KMX_PROF_MERGE); CK(launch_dense_solid((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, Wb * partition, si, max_n, ctx->st, &ctx->launches)); }
   }
+  PROF(KMX_PROF_MERGE);
   CK(launch_dense_emit((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, mp->recurrence_min, mp->share_min,
-                       Wb * partition, si, (uint8_t*)ctx->body.p, rb, (u64*)ctx->stats.p, max_n, ctx->st, &ctx->launches));
-  ctx->last_body = (uint8_t*)ctx->body.p;
+                       Wb * partition, si, slab, rb, (u64*)ctx->stats.p, max_n, ctx->st, &ctx->launches));
+  ctx->last_body = slab;
   ctx->last_res.n_rows = Wb; ctx->last_res.row_bytes = rb; ctx->last_res.n_union = 0;
   if (mp->format == KMX_FMT_BFT) {
     // W x (8*rb) bits -> (8*rb) x W bits
     CK(ensure(ctx, ctx->body2, slab_bytes + 8));
-    CK(launch_transpose_bits((const uint8_t*)ctx->body.p, Wb, (u64)rb * 8, (uint8_t*)ctx->body2.p, ctx->st, &ctx->launches));
-    ctx->last_body = (uint8_t*)ctx->body2.p;
+    uint8_t* tout = (uint8_t*)ctx->body2.p;
+    if (ctx->merge_out) {
+      if (ctx->merge_out_cap < slab_bytes + 8) return fail(ctx, KMX_ERR_ARG, "merge output buffer too small");
+      tout = (uint8_t*)ctx->merge_out;
+    }
+    { PROF(KMX_PROF_TRANSPOSE); CK(launch_transpose_bits((const uint8_t*)ctx->body.p, Wb, (u64)rb * 8, tout, ctx->st, &ctx->launches)); }
+    ctx->last_body = tout;
     ctx->last_res.n_rows = (u64)rb * 8; ctx->last_res.row_bytes = Wb / 8;
   }
   CK(cudaStreamSynchronize(ctx->st));     // hl / soft host buffers are released on return
@@ -646,5 +689,35 @@ extern "C" int kmx_host_alloc(size_t nbytes, void** host_ptr)
   return cudaMallocHost(host_ptr, nbytes ? nbytes : 1) == cudaSuccess ? KMX_OK : KMX_ERR_NOMEM;
 }
 extern "C" int kmx_host_free(void* host_ptr) { return cudaFreeHost(host_ptr) == cudaSuccess ? KMX_OK : KMX_ERR_CUDA; }
+
+extern "C" int kmx_set_merge_output(kmx_ctx* ctx, void* dev_ptr, size_t cap_bytes)
+{
+  if (!ctx) return KMX_ERR_ARG;
+  ctx->merge_out = dev_ptr; ctx->merge_out_cap = dev_ptr ? cap_bytes : 0;
+  return KMX_OK;
+}
+
+extern "C" int kmx_profile_enable(kmx_ctx* ctx, int on)
+{
+  if (!ctx) return KMX_ERR_ARG;
+  prof_collect(ctx);
+  ctx->prof_on = on != 0;
+  return KMX_OK;
+}
+extern "C" int kmx_profile_reset(kmx_ctx* ctx)
+{
+  if (!ctx) return KMX_ERR_ARG;
+  prof_collect(ctx);
+  for (int i = 0; i < KMX_PROF_KINDS; i++) { ctx->prof_ms[i] = 0; ctx->prof_cnt[i] = 0; }
+  return KMX_OK;
+}
+extern "C" int kmx_profile_get(kmx_ctx* ctx, int kind, double* total_ms, uint64_t* count)
+{
+  if (!ctx || kind < 0 || kind >= KMX_PROF_KINDS) return KMX_ERR_ARG;
+  prof_collect(ctx);
+  if (total_ms) *total_ms = ctx->prof_ms[kind];
+  if (count) *count = ctx->prof_cnt[kind];
+  return KMX_OK;
+}
 
 #include "kmx_generic.inl"

@@ -23,16 +23,19 @@ static int count_generic(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
   c.bcnt = ctx->d_cursor; c.max_bcnt = *std::max_element(ctx->h_cursor.begin(), ctx->h_cursor.end());
   u64 mlo = 0, mhi = 0; const u64 Wb = ctx->prm.window_bits;
   if (hash) fastmod_magic(Wb, mlo, mhi);
-  CK(launch_expand_keys(c, hash ? 1 : 0, Wb, Wb, mlo, mhi, d_koff, d_kcur, (u64*)ctx->keys_lo.p, (u64*)ctx->keys_hi.p, ctx->st, &ctx->launches));
+  { PROF(KMX_PROF_EXPAND);
+  CK(launch_expand_keys(c, hash ? 1 : 0, Wb, Wb, mlo, mhi, d_koff, d_kcur, (u64*)ctx->keys_lo.p, (u64*)ctx->keys_hi.p, ctx->st, &ctx->launches)); }
   const size_t wb = std::max(radix_sort_work_bytes(P, koff.data()), rle_work_bytes(P, koff.data()));
   CK(ensure(ctx, ctx->sort_work, wb));
   const int end_bit = hash ? bit_length(Wb * P - 1) : 2 * (int)ctx->prm.kmer_size;
   int in_alt = 0;
+  { PROF(KMX_PROF_SORT);
   CK(segmented_radix_sort(P, koff.data(), (u64*)ctx->keys_lo.p, (u64*)ctx->keys_hi.p, (u64*)ctx->keys_lo2.p, (u64*)ctx->keys_hi2.p,
-                          KW, 0, end_bit, ctx->sort_work.p, &in_alt, ctx->st, &ctx->launches));
+                          KW, 0, end_bit, ctx->sort_work.p, &in_alt, ctx->st, &ctx->launches)); }
   const u64* slo = (const u64*)(in_alt ? ctx->keys_lo2.p : ctx->keys_lo.p);
   const u64* shi = (const u64*)(in_alt ? ctx->keys_hi2.p : ctx->keys_hi.p);
   std::vector<u64> toff, soff;
+  PROF(KMX_PROF_RLE);
   CK(rle_segments(P, koff.data(), slo, shi, KW, hard_min, ctx->sort_work.p, toff, soff, 0, nullptr, nullptr, nullptr, ctx->st, &ctx->launches));
   const u64 D = soff[P];
   void *kp = nullptr, *hp = nullptr, *cp = nullptr;
@@ -50,6 +53,7 @@ static int count_generic(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
 static int merge_sparse(kmx_ctx* ctx, uint32_t partition, const kmx_merge_params* mp, kmx_merge_result* res,
                         const std::vector<MergeList>& hl, u64 max_n, u64 tot_n)
 {
+  PROF(KMX_PROF_MERGE);
   const u32 N = ctx->prm.nb_samples;
   const bool hash = ctx->prm.key_kind == KMX_KEY_HASH;
   const int KW = hash ? 1 : ctx->W;

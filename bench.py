@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--hard-min", type=int, default=2)
     ap.add_argument("--kmer-size", type=int, default=31)
     ap.add_argument("--mode", default="hash:bf:bin")
+    ap.add_argument("--lanes", type=int, default=4, help="samples in flight (kmx_run_samples lanes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-samples", type=int, default=4, help="samples in the bounded CPU-reference run")
@@ -286,18 +287,28 @@ def main_kmx(args):
         wall[name] = wall.get(name, 0.0) + time.perf_counter() - t0
         ck(rc, name)
 
-    def step_device():
-        tm("reset", L.kmx_reset, h)
-        for s in range(N):
-            tm("begin", L.kmx_superk_begin, h)
-            tm("push", L.kmx_superk_push_fastq, h, d_text.value + s * sample_bytes, sample_bytes, 1)
-            tm("end", L.kmx_superk_end, h, None)
-            tm("count", L.kmx_count_sample, h, s, args.hard_min)
+    dev_ptrs = (C.c_void_p * N)(*[d_text.value + s * sample_bytes for s in range(N)])
+    sizes = (C.c_size_t * N)(*([sample_bytes] * N))
+    hmins = (C.c_uint32 * N)(*([args.hard_min] * N))
+
+    def merges(to_host=None):
         for p in range(P):
-            if fmt in ("bf", "bft"):
+            if to_host is None and fmt in ("bf", "bft"):
                 tm("set_out", L.kmx_set_merge_output, h, d_out.value + p * (slab_bytes + 64), slab_bytes + 64)
             tm("merge", L.kmx_merge_partition, h, p, C.byref(mp), C.byref(res))
+            if to_host is not None:
+                tm("merge_get", L.kmx_merge_get, h, to_host + p * slab_bytes, None, None)
         tm("set_out", L.kmx_set_merge_output, h, None, 0)
+
+    def make_step(ptrs, on_device, lanes, to_host=None):
+        def step():
+            tm("reset", L.kmx_reset, h)
+            tm("run_samples", L.kmx_run_samples, h, N, ptrs, sizes, on_device, None, hmins, lanes, None)
+            merges(to_host)
+        return step
+
+    step_device = make_step(dev_ptrs, 1, args.lanes)
+    step_device_1lane = make_step(dev_ptrs, 1, 1)
 
     def barrier():
         if world > 1:
@@ -313,7 +324,7 @@ def main_kmx(args):
         ev0.record(stream)
         for _ in range(steps):
             fn()
-        ev1.record(stream)
+        ev1.record(stream)          # lane 0's stream; every merge waits for all lanes first
         barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
@@ -324,8 +335,6 @@ def main_kmx(args):
 
     for _ in range(args.warmup):
         step_device()
-    ck(L.kmx_profile_enable(h, 1), "prof")
-    ck(L.kmx_profile_reset(h), "prof")
     launches0 = L.kmx_launch_count(h)
     wall.clear()
     sampler = ClockSampler(local)
@@ -334,15 +343,23 @@ def main_kmx(args):
     clocks = sampler.stop()
     host_wall = {k: round(1e3 * v / args.steps, 2) for k, v in wall.items()}
     launches = (L.kmx_launch_count(h) - launches0) // max(args.steps, 1)
+    ms_step = ms / args.steps
+    value = world * kmers_step / (ms_step * 1e-3)
+
+    # per-kernel device time: same step, ONE lane (kernels back to back on one stream, so the
+    # CUDA-event spans around each launch are exclusive), events recorded inside the library
+    step_device_1lane()
+    ck(L.kmx_profile_enable(h, 1), "prof")
+    ck(L.kmx_profile_reset(h), "prof")
+    psteps = max(1, min(args.steps, 2))
+    ms_1lane = timed(step_device_1lane, psteps) / psteps
     prof = {}
     for i, name in enumerate(_lib.PROF_KINDS):
         tms = C.c_double(); cnt = C.c_uint64()
         ck(L.kmx_profile_get(h, i, C.byref(tms), C.byref(cnt)), "prof_get")
         if cnt.value:
-            prof[name] = {"ms_per_step": tms.value / args.steps, "launches_per_step": cnt.value // args.steps}
+            prof[name] = {"ms_per_step": tms.value / psteps, "launches_per_step": cnt.value // psteps}
     ck(L.kmx_profile_enable(h, 0), "prof")
-    ms_step = ms / args.steps
-    value = world * kmers_step / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (device time share from the event spans)
     peaks = {}
@@ -382,26 +399,16 @@ def main_kmx(args):
             e2e = {"value": None, "unit": "k-mers/s", "error": "pinned host allocation failed"}
         else:
             ck(L.kmx_memcpy_d2h(h, h_text, d_text, N * sample_bytes), "d2h text")
-            d2h = 0
-
-            def step_host():
-                ck(L.kmx_reset(h), "reset")
-                for s in range(N):
-                    ck(L.kmx_superk_begin(h), "begin")
-                    ck(L.kmx_superk_push_fastq(h, h_text.value + s * sample_bytes, sample_bytes, 0), "push")
-                    ck(L.kmx_superk_end(h, None), "end")
-                    ck(L.kmx_count_sample(h, s, args.hard_min), "count")
-                for p in range(P):
-                    ck(L.kmx_merge_partition(h, p, C.byref(mp), C.byref(res)), "merge")
-                    ck(L.kmx_merge_get(h, h_out.value + p * slab_bytes, None, None), "merge_get")
-
+            host_ptrs = (C.c_void_p * N)(*[h_text.value + s * sample_bytes for s in range(N)])
+            step_host = make_step(host_ptrs, 0, args.lanes, to_host=h_out.value)
             step_host()
-            t0 = time.perf_counter()
-            ms_e = timed(step_host, max(1, min(args.steps, 2)))
-            wall = time.perf_counter() - t0
             ns = max(1, min(args.steps, 2))
+            t0 = time.perf_counter()
+            ms_e = timed(step_host, ns)
+            wall_e = time.perf_counter() - t0
             e2e = {"value": world * kmers_step / (ms_e / ns * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": N * sample_bytes,
-                   "d2h_bytes_per_step": P * slab_bytes, "ms_per_step": ms_e / ns, "wall_s_per_step": wall / ns}
+                   "d2h_bytes_per_step": P * slab_bytes, "ms_per_step": ms_e / ns, "wall_s_per_step": wall_e / ns,
+                   "what": "kmx_run_samples on pinned host FASTQ + kmx_merge_partition/kmx_merge_get into pinned host memory"}
             L.kmx_host_free(h_text); L.kmx_host_free(h_out)
 
     cpu = None
@@ -416,9 +423,9 @@ def main_kmx(args):
                                        f"P={P}, bloom={args.bloom_size}, hard-min {args.hard_min}, --static-repart, m=10"
                                        + (f"; per GPU, {world} GPUs" if world > 1 else ""),
                            "kmers_per_step": kmers_step, "l2": "inputs larger than L2 (315 MB text per launch)",
-                           "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM"},
+                           "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM", "lanes": args.lanes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in prof.items()},
+                "kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in prof.items()}, "ms_per_step_1lane": ms_1lane,
                 "host_wall_ms_per_step": host_wall, "device_bytes": int(L.kmx_device_bytes(h))}
         print(json.dumps(line))
     eng.close()

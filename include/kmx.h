@@ -85,6 +85,15 @@ int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition);
  * the sample just finished by kmx_superk_end, the ascending list of (key, count >= hard_min),
  * counts saturating at 2^32-1.  The lists stay in HBM under slot `sample`.                   */
 int kmx_count_sample(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min);
+/* Stage 1 + 2 for many samples in one call (what TaskScheduler::exec_superk_count,
+ * task_scheduler.hpp:251-348, does with its thread pool): sample i is the strict 4-line FASTQ
+ * block texts[i] (nbytes[i] bytes, host or device per on_device), counted with hard_min[i]
+ * into slot sample_ids[i] (NULL = i).  `nlanes` (1..8) samples are in flight at once, each on
+ * its own CUDA stream, so host->device copies and small read-backs overlap other samples'
+ * kernels.  kmers_per_partition (n*P, may be NULL) receives every sample's .pinfo vector.     */
+int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* texts, const size_t* nbytes, int on_device,
+                    const uint32_t* sample_ids, const uint32_t* hard_min, uint32_t nlanes,
+                    uint64_t* kmers_per_partition);
 /* size of / copy out one list == body of counts/partition_P/<id>.kmer|.hash
  * keys: n*w u64 (w = 1 for hash keys), counts: n u32.                                        */
 int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n);

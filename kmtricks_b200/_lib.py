@@ -43,6 +43,7 @@ SYMBOLS = {
     "kmx_superk_push_reads": (_i, [_vp, _vp, C.POINTER(_u64), _sz]),
     "kmx_superk_end": (_i, [_vp, C.POINTER(_u64)]),
     "kmx_count_sample": (_i, [_vp, _u32, _u32]),
+    "kmx_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u32), _u32, C.POINTER(_u64)]),
     "kmx_counts_size": (_i, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "kmx_counts_get": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "kmx_counts_put": (_i, [_vp, _u32, _u32, _vp, _vp, _u64]),

@@ -1,13 +1,17 @@
-// kmx_api.cu -- the C ABI (include/kmx.h): context, device memory, stage drivers.
+// kmx_api.cu -- the C ABI (include/kmx.h): context, lanes, device memory, stage drivers.
 #include "../../include/kmx.h"
 #include "common.cuh"
 #include "kmx_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace kmx;
@@ -33,9 +37,7 @@ cudaError_t launch_sparse_emit(const MergeList* d_lists, u32 N, const u32* d_sof
 
 namespace {
 
-struct DBuf {
-  void* p = nullptr; size_t cap = 0;
-};
+struct DBuf { void* p = nullptr; size_t cap = 0; };
 
 struct ListRef {            // one (sample, partition) list in HBM
   u64* lo = nullptr; u64* hi = nullptr; u32* cnt = nullptr; u64 n = 0;
@@ -47,24 +49,17 @@ struct ProfSpan { cudaEvent_t a, b; int kind; };
 
 }  // namespace
 
-struct kmx_ctx {
-  int device = 0;
-  kmx_params prm{};
-  int W = 1;                       // words per k-mer
-  int wlen = 0, max_nk = 0;
+struct kmx_ctx;
+
+// A lane owns everything one in-flight sample needs (stream, text staging, line index, bucket
+// slab, histogram, sort scratch).  Lane 0 also serves the single-sample API and the merges;
+// kmx_run_samples drives several lanes from host threads so that the H2D copy and the small
+// host round-trips of one sample overlap the kernels of the others.
+struct Lane {
+  kmx_ctx* ctx = nullptr; int id = 0;
   cudaStream_t st = nullptr;
   std::string err;
   u64 launches = 0;
-  u64 dev_bytes = 0;
-  std::vector<void*> user_allocs;
-  bool prof_on = false;
-  std::vector<ProfSpan> prof_spans;
-  std::vector<cudaEvent_t> prof_pool;
-  double prof_ms[KMX_PROF_KINDS] = {0};
-  u64 prof_cnt[KMX_PROF_KINDS] = {0};
-  void* merge_out = nullptr; size_t merge_out_cap = 0;
-
-  uint16_t* d_repart = nullptr;
   // ---- stage 1
   DBuf text, seq_start, seq_len, tile_counts, tile_prefix;
   u64* d_total = nullptr;          // 1 u64
@@ -73,55 +68,86 @@ struct kmx_ctx {
   u64* d_boff = nullptr; u32* d_bcap = nullptr; u32* d_cursor = nullptr; u64* d_kcnt = nullptr;
   std::vector<u64> h_boff; std::vector<u32> h_bcap, h_cursor; std::vector<u64> h_kcnt;
   bool in_sample = false, sample_ready = false;
+  char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
   DBuf hist, sub_counts, sub_off;
-  DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, rle_tiles;
+  DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt;
+  // ---- profiling
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+struct kmx_ctx {
+  int device = 0;
+  kmx_params prm{};
+  int W = 1;                       // words per k-mer
+  int wlen = 0, max_nk = 0;
+  std::string err;
+  std::mutex mu;                   // arena, err, dev_bytes
+  u64 dev_bytes = 0;
+  std::vector<void*> user_allocs;
+  int hist_ok = -1;
+  bool prof_on = false;
+  double prof_ms[KMX_PROF_KINDS] = {0};
+  u64 prof_cnt[KMX_PROF_KINDS] = {0};
+  void* merge_out = nullptr; size_t merge_out_cap = 0;
+  uint16_t* d_repart = nullptr;
+  std::vector<std::unique_ptr<Lane>> lanes;
   std::vector<ArenaBlock> arena;
   std::vector<ListRef> lists;      // [N*P]
-  // ---- stage 3
-  DBuf d_lists, d_soft, solid_in, body, stats, keep, out_row, row_keep, uni_lo, uni_hi, uni_lo2, uni_hi2, scan_work, tmp_cnt;
+  // ---- stage 3 (on lane 0's stream)
+  DBuf d_lists, d_soft, solid_in, body, body2, stats, keep, out_row, row_keep, uni_lo, uni_hi, uni_lo2, uni_hi2, scan_work;
   kmx_merge_result last_res{};
   u32 last_emit_all = 0;
-  uint8_t* last_body = nullptr;    // where the final body lives (body or body2)
-  DBuf body2;
+  uint8_t* last_body = nullptr;    // where the final body lives
 };
 
 // ---------------------------------------------------------------------------------------
-static int fail(kmx_ctx* c, int code, const char* fmt, ...)
+static int fail(Lane* ln, int code, const char* fmt, ...)
 {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-  if (c) c->err = buf;
+  if (ln) {
+    ln->err = buf;
+    std::lock_guard<std::mutex> g(ln->ctx->mu);
+    ln->ctx->err = buf;
+  }
   return code;
 }
-static cudaEvent_t prof_event(kmx_ctx* c)
+
+static cudaEvent_t prof_event(Lane* ln)
 {
   cudaEvent_t e;
-  if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  if (!ln->prof_pool.empty()) { e = ln->prof_pool.back(); ln->prof_pool.pop_back(); return e; }
   cudaEventCreate(&e);
   return e;
 }
 struct ProfScope {
-  kmx_ctx* c; ProfSpan s; bool on;
-  ProfScope(kmx_ctx* c_, int kind) : c(c_), on(c_->prof_on) { if (on) { s.kind = kind; s.a = prof_event(c); s.b = prof_event(c); cudaEventRecord(s.a, c->st); } }
-  ~ProfScope() { if (on) { cudaEventRecord(s.b, c->st); c->prof_spans.push_back(s); } }
+  Lane* ln; ProfSpan s; bool on;
+  ProfScope(Lane* l, int kind) : ln(l), on(l->ctx->prof_on) { if (on) { s.kind = kind; s.a = prof_event(ln); s.b = prof_event(ln); cudaEventRecord(s.a, ln->st); } }
+  ~ProfScope() { if (on) { cudaEventRecord(s.b, ln->st); ln->prof_spans.push_back(s); } }
 };
-#define PROF(kind) ProfScope prof_scope_##kind(ctx, kind)
+#define PROF(kind) ProfScope prof_scope_##kind(ln, kind)
 static void prof_collect(kmx_ctx* c)
 {
-  if (c->prof_spans.empty()) return;
-  cudaStreamSynchronize(c->st);
-  for (auto& s : c->prof_spans) {
-    float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
-    c->prof_ms[s.kind] += ms; c->prof_cnt[s.kind] += 1;
-    c->prof_pool.push_back(s.a); c->prof_pool.push_back(s.b);
+  for (auto& lp : c->lanes) {
+    Lane* ln = lp.get();
+    if (ln->prof_spans.empty()) continue;
+    cudaStreamSynchronize(ln->st);
+    for (auto& s : ln->prof_spans) {
+      float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
+      c->prof_ms[s.kind] += ms; c->prof_cnt[s.kind] += 1;
+      ln->prof_pool.push_back(s.a); ln->prof_pool.push_back(s.b);
+    }
+    ln->prof_spans.clear();
   }
-  c->prof_spans.clear();
 }
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMX_ERR_NOMEM : KMX_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ln, e_ == cudaErrorMemoryAllocation ? KMX_ERR_NOMEM : KMX_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-static cudaError_t ensure(kmx_ctx* ctx, DBuf& b, size_t bytes, bool keep = false)
+static void add_bytes(kmx_ctx* ctx, long long d) { std::lock_guard<std::mutex> g(ctx->mu); ctx->dev_bytes = (u64)((long long)ctx->dev_bytes + d); }
+
+static cudaError_t ensure(Lane* ln, DBuf& b, size_t bytes)
 {
   if (bytes <= b.cap) return cudaSuccess;
   size_t ncap = std::max(bytes, b.cap + b.cap / 2);
@@ -129,17 +155,25 @@ static cudaError_t ensure(kmx_ctx* ctx, DBuf& b, size_t bytes, bool keep = false
   void* np = nullptr;
   cudaError_t e = cudaMalloc(&np, ncap);
   if (e != cudaSuccess) return e;
-  if (b.p) {
-    if (keep) { e = cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->st); if (e != cudaSuccess) return e; cudaStreamSynchronize(ctx->st); }
-    cudaFree(b.p); ctx->dev_bytes -= b.cap;
-  }
-  b.p = np; b.cap = ncap; ctx->dev_bytes += ncap;
+  if (b.p) { cudaStreamSynchronize(ln->st); cudaFree(b.p); add_bytes(ln->ctx, -(long long)b.cap); }
+  b.p = np; b.cap = ncap; add_bytes(ln->ctx, (long long)ncap);
   return cudaSuccess;
 }
-static void release(kmx_ctx* ctx, DBuf& b) { if (b.p) { cudaFree(b.p); ctx->dev_bytes -= b.cap; } b.p = nullptr; b.cap = 0; }
+static void release(kmx_ctx* ctx, DBuf& b) { if (b.p) { cudaFree(b.p); add_bytes(ctx, -(long long)b.cap); } b.p = nullptr; b.cap = 0; }
+
+static cudaError_t ensure_pin(Lane* ln, size_t bytes)
+{
+  if (bytes <= ln->h_pin_cap) return cudaSuccess;
+  if (ln->h_pin) { cudaStreamSynchronize(ln->st); cudaFreeHost(ln->h_pin); ln->h_pin = nullptr; ln->h_pin_cap = 0; }
+  size_t cap = std::max(bytes, (size_t)1 << 16);
+  cudaError_t e = cudaMallocHost((void**)&ln->h_pin, cap);
+  if (e == cudaSuccess) ln->h_pin_cap = cap;
+  return e;
+}
 
 static cudaError_t arena_alloc(kmx_ctx* ctx, size_t bytes, void** out)
 {
+  std::lock_guard<std::mutex> g(ctx->mu);
   bytes = (bytes + 255) & ~(size_t)255;
   if (bytes == 0) bytes = 256;
   for (auto& b : ctx->arena) if (b.cap - b.used >= bytes) { *out = b.p + b.used; b.used += bytes; return cudaSuccess; }
@@ -164,6 +198,37 @@ static void fastmod_magic(u64 d, u64& mlo, u64& mhi)
   mlo = (u64)M; mhi = (u64)(M >> 64);
 }
 
+// lanes are created on demand; lane 0 at kmx_create
+static int lane_create(kmx_ctx* ctx, int id)
+{
+  std::unique_ptr<Lane> up(new Lane());
+  Lane* ln = up.get();
+  ln->ctx = ctx; ln->id = id;
+  ctx->lanes.push_back(std::move(up));
+  const u32 P = ctx->prm.nb_partitions;
+  CK(cudaStreamCreateWithFlags(&ln->st, cudaStreamNonBlocking));
+  CK(cudaMalloc(&ln->d_total, 8)); CK(cudaMalloc(&ln->d_flags, 16));
+  CK(cudaMalloc(&ln->d_boff, P * 8)); CK(cudaMalloc(&ln->d_bcap, P * 4));
+  CK(cudaMalloc(&ln->d_cursor, P * 4)); CK(cudaMalloc(&ln->d_kcnt, P * 8));
+  ln->h_boff.assign(P, 0); ln->h_bcap.assign(P, 0); ln->h_cursor.assign(P, 0); ln->h_kcnt.assign(P, 0);
+  CK(ensure_pin(ln, (size_t)P * 32 + 256));
+  return KMX_OK;
+}
+static void lane_destroy(Lane* ln)
+{
+  kmx_ctx* ctx = ln->ctx;
+  if (ln->st) cudaStreamSynchronize(ln->st);
+  DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->records, &ln->hist,
+                  &ln->sub_counts, &ln->sub_off, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt};
+  for (DBuf* b : bufs) release(ctx, *b);
+  void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
+  for (void* p : singles) if (p) cudaFree(p);
+  if (ln->h_pin) cudaFreeHost(ln->h_pin);
+  for (auto e : ln->prof_pool) cudaEventDestroy(e);
+  for (auto& s : ln->prof_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  if (ln->st) cudaStreamDestroy(ln->st);
+}
+
 // ---------------------------------------------------------------------------------------
 extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
 {
@@ -172,240 +237,243 @@ extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
   kmx_ctx* ctx = new kmx_ctx();
   *out = ctx;                                   // returned even on failure so the caller can read the error
   ctx->device = device; ctx->prm = *prm;
+  Lane tmp; tmp.ctx = ctx; Lane* ln = &tmp;     // error sink until lane 0 exists
   const u32 k = prm->kmer_size, m = prm->minim_size;
-  if (k < 8 || k > 63) return fail(ctx, KMX_ERR_ARG, "kmer_size %u unsupported (8..63)", k);
-  if (m < 4 || m > 12 || m > k) return fail(ctx, KMX_ERR_ARG, "minim_size %u unsupported (4..12, <= k)", m);
-  if (prm->nb_partitions < 1 || prm->nb_partitions > 65535) return fail(ctx, KMX_ERR_ARG, "nb_partitions %u unsupported", prm->nb_partitions);
-  if (!prm->repart_table) return fail(ctx, KMX_ERR_ARG, "repart_table is NULL");
-  if (prm->nb_samples < 1) return fail(ctx, KMX_ERR_ARG, "nb_samples must be >= 1");
-  if (prm->key_kind == KMX_KEY_HASH && (prm->window_bits == 0 || prm->window_bits % 64)) return fail(ctx, KMX_ERR_ARG, "window_bits must be a positive multiple of 64");
-  if (prm->key_kind > KMX_KEY_HASH) return fail(ctx, KMX_ERR_ARG, "bad key_kind");
+  if (k < 8 || k > 63) return fail(ln, KMX_ERR_ARG, "kmer_size %u unsupported (8..63)", k);
+  if (m < 4 || m > 12 || m > k) return fail(ln, KMX_ERR_ARG, "minim_size %u unsupported (4..12, <= k)", m);
+  if (prm->nb_partitions < 1 || prm->nb_partitions > 65535) return fail(ln, KMX_ERR_ARG, "nb_partitions %u unsupported", prm->nb_partitions);
+  if (!prm->repart_table) return fail(ln, KMX_ERR_ARG, "repart_table is NULL");
+  if (prm->nb_samples < 1) return fail(ln, KMX_ERR_ARG, "nb_samples must be >= 1");
+  if (prm->key_kind == KMX_KEY_HASH && (prm->window_bits == 0 || prm->window_bits % 64)) return fail(ln, KMX_ERR_ARG, "window_bits must be a positive multiple of 64");
+  if (prm->key_kind > KMX_KEY_HASH) return fail(ln, KMX_ERR_ARG, "bad key_kind");
   ctx->W = (k + 31) / 32;
   ctx->wlen = (int)(k - m + 1);
   ctx->max_nk = (ctx->W == 1 ? KMX_REC1_MAXN : KMX_REC2_MAXN) - (int)k + 1;
   if (s1_smem_bytes(ctx->W, 2048, ctx->wlen, prm->nb_partitions) > 200 * 1024)
-    return fail(ctx, KMX_ERR_ARG, "nb_partitions %u too large for the stage-1 staging layout", prm->nb_partitions);
+    return fail(ln, KMX_ERR_ARG, "nb_partitions %u too large for the stage-1 staging layout", prm->nb_partitions);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev <= device) return fail(ctx, KMX_ERR_CUDA, "no usable CUDA device %d (%s)", device, cudaGetErrorString(e));
+  if (e != cudaSuccess || ndev <= device) return fail(ln, KMX_ERR_CUDA, "no usable CUDA device %d (%s)", device, cudaGetErrorString(e));
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(ctx, KMX_ERR_CUDA, "device %d is sm_%d%d; libkmx_sm100 needs sm_100", device, prop.major, prop.minor);
-  CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+  if (prop.major < 10) return fail(ln, KMX_ERR_CUDA, "device %d is sm_%d%d; libkmx_sm100 needs sm_100", device, prop.major, prop.minor);
   const size_t tn = (size_t)1 << (2 * m);
+  for (size_t i = 0; i < tn; i++) if (prm->repart_table[i] >= prm->nb_partitions) return fail(ln, KMX_ERR_ARG, "repart_table[%zu]=%u >= nb_partitions", i, prm->repart_table[i]);
   CK(cudaMalloc(&ctx->d_repart, tn * 2)); ctx->dev_bytes += tn * 2;
-  for (size_t i = 0; i < tn; i++) if (prm->repart_table[i] >= prm->nb_partitions) return fail(ctx, KMX_ERR_ARG, "repart_table[%zu]=%u >= nb_partitions", i, prm->repart_table[i]);
-  CK(cudaMemcpyAsync(ctx->d_repart, prm->repart_table, tn * 2, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaMemcpy(ctx->d_repart, prm->repart_table, tn * 2, cudaMemcpyHostToDevice));
   ctx->prm.repart_table = nullptr;
-  const u32 P = prm->nb_partitions;
-  CK(cudaMalloc(&ctx->d_total, 8)); CK(cudaMalloc(&ctx->d_flags, 16));
-  CK(cudaMalloc(&ctx->d_boff, P * 8)); CK(cudaMalloc(&ctx->d_bcap, P * 4));
-  CK(cudaMalloc(&ctx->d_cursor, P * 4)); CK(cudaMalloc(&ctx->d_kcnt, P * 8));
-  ctx->h_boff.assign(P, 0); ctx->h_bcap.assign(P, 0); ctx->h_cursor.assign(P, 0); ctx->h_kcnt.assign(P, 0);
-  ctx->lists.assign((size_t)prm->nb_samples * P, ListRef());
+  ctx->lists.assign((size_t)prm->nb_samples * prm->nb_partitions, ListRef());
+  int rc = lane_create(ctx, 0);
+  if (rc) return rc;
   return KMX_OK;
 }
 
 extern "C" void kmx_destroy(kmx_ctx* ctx)
 {
   if (!ctx) return;
-  if (ctx->st) {
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->st);
-    DBuf* bufs[] = {&ctx->text, &ctx->seq_start, &ctx->seq_len, &ctx->tile_counts, &ctx->tile_prefix, &ctx->records,
-                    &ctx->hist, &ctx->sub_counts, &ctx->sub_off, &ctx->keys_lo, &ctx->keys_hi, &ctx->keys_lo2, &ctx->keys_hi2,
-                    &ctx->sort_work, &ctx->rle_tiles, &ctx->d_lists, &ctx->d_soft, &ctx->solid_in, &ctx->body, &ctx->stats,
-                    &ctx->keep, &ctx->out_row, &ctx->row_keep, &ctx->uni_lo, &ctx->uni_hi, &ctx->uni_lo2, &ctx->uni_hi2,
-                    &ctx->scan_work, &ctx->tmp_cnt, &ctx->body2};
-    for (DBuf* b : bufs) release(ctx, *b);
-    arena_clear(ctx);
-    for (void* p : ctx->user_allocs) cudaFree(p);
-    void* singles[] = {ctx->d_repart, ctx->d_total, ctx->d_flags, ctx->d_boff, ctx->d_bcap, ctx->d_cursor, ctx->d_kcnt};
-    for (void* p : singles) if (p) cudaFree(p);
-    cudaStreamDestroy(ctx->st);
-  }
+  cudaSetDevice(ctx->device);
+  for (auto& lp : ctx->lanes) lane_destroy(lp.get());
+  DBuf* bufs[] = {&ctx->d_lists, &ctx->d_soft, &ctx->solid_in, &ctx->body, &ctx->body2, &ctx->stats, &ctx->keep, &ctx->out_row,
+                  &ctx->row_keep, &ctx->uni_lo, &ctx->uni_hi, &ctx->uni_lo2, &ctx->uni_hi2, &ctx->scan_work};
+  for (DBuf* b : bufs) release(ctx, *b);
+  arena_clear(ctx);
+  for (void* p : ctx->user_allocs) cudaFree(p);
+  if (ctx->d_repart) cudaFree(ctx->d_repart);
   delete ctx;
 }
 
+#define LANE0 Lane* ln = ctx->lanes.empty() ? nullptr : ctx->lanes[0].get(); if (!ln) return KMX_ERR_STATE
+
 extern "C" const char* kmx_last_error(const kmx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" uint64_t kmx_launch_count(const kmx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t kmx_launch_count(const kmx_ctx* ctx)
+{
+  if (!ctx) return 0;
+  u64 t = 0; for (auto& l : ctx->lanes) t += l->launches;
+  return t;
+}
 extern "C" uint64_t kmx_device_bytes(const kmx_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
-extern "C" void* kmx_stream(kmx_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
-extern "C" int kmx_sync(kmx_ctx* ctx) { if (!ctx) return KMX_ERR_ARG; CK(cudaStreamSynchronize(ctx->st)); return KMX_OK; }
+extern "C" void* kmx_stream(kmx_ctx* ctx) { return (ctx && !ctx->lanes.empty()) ? (void*)ctx->lanes[0]->st : nullptr; }
+extern "C" int kmx_sync(kmx_ctx* ctx)
+{
+  if (!ctx) return KMX_ERR_ARG;
+  for (auto& lp : ctx->lanes) { Lane* ln = lp.get(); CK(cudaStreamSynchronize(ln->st)); }
+  return KMX_OK;
+}
 
 extern "C" int kmx_reset(kmx_ctx* ctx)
 {
   if (!ctx) return KMX_ERR_ARG;
-  CK(cudaStreamSynchronize(ctx->st));
+  int rc = kmx_sync(ctx);
+  if (rc) return rc;
   for (auto& b : ctx->arena) b.used = 0;          // keep the blocks: no cudaFree/cudaMalloc per step
   for (auto& l : ctx->lists) l = ListRef();
-  ctx->in_sample = ctx->sample_ready = false;
+  for (auto& lp : ctx->lanes) lp->in_sample = lp->sample_ready = false;
   return KMX_OK;
 }
 
 // ---------------------------------------------------------------------------------------
 // stage 1
 // ---------------------------------------------------------------------------------------
-static int upload_bucket_meta(kmx_ctx* ctx)
+static int upload_bucket_meta(Lane* ln)
 {
-  const u32 P = ctx->prm.nb_partitions;
-  CK(cudaMemcpyAsync(ctx->d_boff, ctx->h_boff.data(), P * 8, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemcpyAsync(ctx->d_bcap, ctx->h_bcap.data(), P * 4, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemcpyAsync(ctx->d_cursor, ctx->h_cursor.data(), P * 4, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemcpyAsync(ctx->d_kcnt, ctx->h_kcnt.data(), P * 8, cudaMemcpyHostToDevice, ctx->st));
+  const u32 P = ln->ctx->prm.nb_partitions;
+  // stage through the pinned scratch so the copies are truly asynchronous
+  char* hp = ln->h_pin;
+  memcpy(hp, ln->h_boff.data(), P * 8); memcpy(hp + P * 8, ln->h_kcnt.data(), P * 8);
+  memcpy(hp + P * 16, ln->h_bcap.data(), P * 4); memcpy(hp + P * 20, ln->h_cursor.data(), P * 4);
+  CK(cudaMemcpyAsync(ln->d_boff, hp, P * 8, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemcpyAsync(ln->d_kcnt, hp + P * 8, P * 8, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemcpyAsync(ln->d_bcap, hp + P * 16, P * 4, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemcpyAsync(ln->d_cursor, hp + P * 20, P * 4, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaStreamSynchronize(ln->st));             // the scratch is reused right away
   return KMX_OK;
 }
 
-// make room for `extra[p]` more records in every partition (keeps what is there)
-static int grow_buckets(kmx_ctx* ctx, const std::vector<u64>& need /* total records wanted per partition */)
+// make room for need[p] records in every partition (keeps what is there)
+static int grow_buckets(Lane* ln, const std::vector<u64>& need)
 {
+  kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   const size_t rec = ctx->W == 1 ? 16 : 32;
   bool ok = true;
-  for (u32 p = 0; p < P; p++) if (need[p] > ctx->h_bcap[p]) ok = false;
+  for (u32 p = 0; p < P; p++) if (need[p] > ln->h_bcap[p]) ok = false;
   if (ok) return KMX_OK;
   std::vector<u64> nboff(P); std::vector<u32> ncap(P);
   u64 tot = 0;
   for (u32 p = 0; p < P; p++) {
-    u64 c = std::max<u64>(need[p], ctx->h_bcap[p]);
+    u64 c = std::max<u64>(need[p], ln->h_bcap[p]);
     c = (c + 63) & ~(u64)63;
-    if (c > 0xFFFFFFF0ULL) return fail(ctx, KMX_ERR_NOMEM, "partition %u needs %llu records (> 2^32)", p, (unsigned long long)c);
+    if (c > 0xFFFFFFF0ULL) return fail(ln, KMX_ERR_NOMEM, "partition %u needs %llu records (> 2^32)", p, (unsigned long long)c);
     nboff[p] = tot; ncap[p] = (u32)c; tot += c;
   }
   DBuf nb;
   cudaError_t e = cudaMalloc(&nb.p, tot * rec + 256);
-  if (e != cudaSuccess) return fail(ctx, KMX_ERR_NOMEM, "bucket slab of %llu bytes: %s", (unsigned long long)(tot * rec), cudaGetErrorString(e));
-  nb.cap = tot * rec + 256; ctx->dev_bytes += nb.cap;
-  if (ctx->records.p) {
-    for (u32 p = 0; p < P; p++) if (ctx->h_cursor[p])
-      CK(cudaMemcpyAsync((char*)nb.p + nboff[p] * rec, (char*)ctx->records.p + ctx->h_boff[p] * rec,
-                         (size_t)std::min<u64>(ctx->h_cursor[p], ctx->h_bcap[p]) * rec, cudaMemcpyDeviceToDevice, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    release(ctx, ctx->records);
+  if (e != cudaSuccess) return fail(ln, KMX_ERR_NOMEM, "bucket slab of %llu bytes: %s", (unsigned long long)(tot * rec), cudaGetErrorString(e));
+  nb.cap = tot * rec + 256; add_bytes(ctx, (long long)nb.cap);
+  if (ln->records.p) {
+    for (u32 p = 0; p < P; p++) if (ln->h_cursor[p])
+      CK(cudaMemcpyAsync((char*)nb.p + nboff[p] * rec, (char*)ln->records.p + ln->h_boff[p] * rec,
+                         (size_t)std::min<u64>(ln->h_cursor[p], ln->h_bcap[p]) * rec, cudaMemcpyDeviceToDevice, ln->st));
+    CK(cudaStreamSynchronize(ln->st));
+    release(ctx, ln->records);
   }
-  ctx->records = nb; ctx->h_boff = nboff; ctx->h_bcap = ncap;
+  ln->records = nb; ln->h_boff = nboff; ln->h_bcap = ncap;
   return KMX_OK;
 }
 
-extern "C" int kmx_superk_begin(kmx_ctx* ctx)
+static int superk_begin(Lane* ln)
 {
-  if (!ctx) return KMX_ERR_ARG;
-  const u32 P = ctx->prm.nb_partitions;
-  std::fill(ctx->h_cursor.begin(), ctx->h_cursor.end(), 0u);
-  std::fill(ctx->h_kcnt.begin(), ctx->h_kcnt.end(), 0ull);
-  (void)P;
-  int rc = upload_bucket_meta(ctx);            // device cursors start at zero even with no push
+  std::fill(ln->h_cursor.begin(), ln->h_cursor.end(), 0u);
+  std::fill(ln->h_kcnt.begin(), ln->h_kcnt.end(), 0ull);
+  int rc = upload_bucket_meta(ln);             // device cursors start at zero even with no push
   if (rc) return rc;
-  ctx->in_sample = true; ctx->sample_ready = false;
+  ln->in_sample = true; ln->sample_ready = false;
   return KMX_OK;
 }
 
 // run stage 1 over nseg segments described by (d_start, d_len) into the buckets; retries
 // with exact capacities when a bucket overflowed.
-static int run_s1(kmx_ctx* ctx, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers)
+static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers)
 {
+  kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   // optimistic capacity: ~1 record per 8 k-mers, 30% head-room for partition imbalance
   std::vector<u64> need(P);
-  for (u32 p = 0; p < P; p++) need[p] = (u64)ctx->h_cursor[p] + (u64)((double)est_kmers / 8.0 / P * 1.3) + 1024;
+  for (u32 p = 0; p < P; p++) need[p] = (u64)ln->h_cursor[p] + (u64)((double)est_kmers / 8.0 / P * 1.3) + 1024;
   for (int attempt = 0; attempt < 3; attempt++) {
-    int rc = grow_buckets(ctx, need);
+    int rc = grow_buckets(ln, need);
     if (rc) return rc;
-    rc = upload_bucket_meta(ctx);
+    rc = upload_bucket_meta(ln);
     if (rc) return rc;
-    CK(cudaMemsetAsync(ctx->d_flags + 2, 0, 4, ctx->st));
+    CK(cudaMemsetAsync(ln->d_flags + 2, 0, 4, ln->st));
     S1Args a;
     a.text = d_text; a.text_bytes = text_bytes; a.seg_start = d_start; a.seg_len = d_len; a.nseg = nseg;
     a.k = (int)ctx->prm.kmer_size; a.m = (int)ctx->prm.minim_size; a.wlen = ctx->wlen; a.max_nk = ctx->max_nk;
-    a.P = P; a.repart = ctx->d_repart; a.records = ctx->records.p; a.boff = ctx->d_boff; a.bcap = ctx->d_bcap;
-    a.cursor = ctx->d_cursor; a.kcnt = ctx->d_kcnt; a.overflow = ctx->d_flags + 2;
+    a.P = P; a.repart = ctx->d_repart; a.records = ln->records.p; a.boff = ln->d_boff; a.bcap = ln->d_bcap;
+    a.cursor = ln->d_cursor; a.kcnt = ln->d_kcnt; a.overflow = ln->d_flags + 2;
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
-    { PROF(KMX_PROF_S1); CK(launch_s1(ctx->W, a, ctx->st, &ctx->launches)); }
-    std::vector<u32> cur(P); std::vector<u64> kc(P); u32 ovf = 0;
-    CK(cudaMemcpyAsync(cur.data(), ctx->d_cursor, P * 4, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(kc.data(), ctx->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(&ovf, ctx->d_flags + 2, 4, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    if (!ovf) { ctx->h_cursor = cur; ctx->h_kcnt = kc; return KMX_OK; }
+    { PROF(KMX_PROF_S1); CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
+    u64* kc = (u64*)ln->h_pin; u32* cur = (u32*)(ln->h_pin + P * 8); u32* ovf = (u32*)(ln->h_pin + P * 12);
+    CK(cudaMemcpyAsync(kc, ln->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ln->st));
+    CK(cudaMemcpyAsync(cur, ln->d_cursor, P * 4, cudaMemcpyDeviceToHost, ln->st));
+    CK(cudaMemcpyAsync(ovf, ln->d_flags + 2, 4, cudaMemcpyDeviceToHost, ln->st));
+    CK(cudaStreamSynchronize(ln->st));
+    if (!*ovf) { ln->h_cursor.assign(cur, cur + P); ln->h_kcnt.assign(kc, kc + P); return KMX_OK; }
     // exact sizes are now known (the cursors kept counting); redo this push from the snapshot
     for (u32 p = 0; p < P; p++) need[p] = (u64)cur[p] + 64;
   }
-  return fail(ctx, KMX_ERR_CUDA, "stage-1 bucket overflow persisted after resize");
+  return fail(ln, KMX_ERR_CUDA, "stage-1 bucket overflow persisted after resize");
 }
 
-extern "C" int kmx_superk_push_fastq(kmx_ctx* ctx, const char* text, size_t nbytes, int on_device)
+static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_device)
 {
-  if (!ctx || (!text && nbytes)) return KMX_ERR_ARG;
-  if (!ctx->in_sample) return fail(ctx, KMX_ERR_STATE, "kmx_superk_push_fastq outside begin/end");
+  if (!ln->in_sample) return fail(ln, KMX_ERR_STATE, "kmx_superk_push_fastq outside begin/end");
   if (nbytes == 0) return KMX_OK;
-  if (nbytes >= 0xFFFFFFF0ULL) return fail(ctx, KMX_ERR_ARG, "text block must be < 4 GiB; split at record boundaries");
+  if (nbytes >= 0xFFFFFFF0ULL) return fail(ln, KMX_ERR_ARG, "text block must be < 4 GiB; split at record boundaries");
   const uint8_t* d_text;
   if (on_device) d_text = (const uint8_t*)text;
   else {
-    CK(ensure(ctx, ctx->text, nbytes + 64));
-    CK(cudaMemcpyAsync(ctx->text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->st));
-    d_text = (const uint8_t*)ctx->text.p;
+    CK(ensure(ln, ln->text, nbytes + 64));
+    CK(cudaMemcpyAsync(ln->text.p, text, nbytes, cudaMemcpyHostToDevice, ln->st));
+    d_text = (const uint8_t*)ln->text.p;
   }
   const u64 ntiles = fq_num_tiles(d_text, nbytes);
-  CK(ensure(ctx, ctx->tile_counts, ntiles * 4));
-  CK(ensure(ctx, ctx->tile_prefix, ntiles * 8));
-  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total, nullptr, nullptr, 0, nullptr, 0, ctx->st, &ctx->launches)); }
-  u64 nl = 0; uint8_t last = 0;
-  CK(cudaMemcpyAsync(&nl, ctx->d_total, 8, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaMemcpyAsync(&last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
-  u64 nlines = nl + (last != '\n' ? 1 : 0);
-  if (nlines % 4) return fail(ctx, KMX_ERR_FORMAT, "FASTQ block has %llu lines (not a multiple of 4)", (unsigned long long)nlines);
+  CK(ensure(ln, ln->tile_counts, ntiles * 4));
+  CK(ensure(ln, ln->tile_prefix, ntiles * 8));
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, ln->d_total, nullptr, nullptr, 0, nullptr, 0, ln->st, &ln->launches)); }
+  u64* nl = (u64*)ln->h_pin; uint8_t* last = (uint8_t*)(ln->h_pin + 8);
+  CK(cudaMemcpyAsync(nl, ln->d_total, 8, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaMemcpyAsync(last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
+  u64 nlines = *nl + (*last != '\n' ? 1 : 0);
+  if (nlines % 4) return fail(ln, KMX_ERR_FORMAT, "FASTQ block has %llu lines (not a multiple of 4)", (unsigned long long)nlines);
   const u64 nrec = nlines / 4;
   if (nrec == 0) return KMX_OK;
-  CK(ensure(ctx, ctx->seq_start, nrec * 4));
-  CK(ensure(ctx, ctx->seq_len, nrec * 4));
-  CK(cudaMemsetAsync(ctx->d_flags, 0, 8, ctx->st));
-  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ctx->tile_counts.p, (u64*)ctx->tile_prefix.p, ctx->d_total,
-                     (u32*)ctx->seq_start.p, (u32*)ctx->seq_len.p, nrec, ctx->d_flags, 1, ctx->st, &ctx->launches)); }
-  u32 fl[2] = {0, 0};
-  CK(cudaMemcpyAsync(fl, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
-  if (fl[0]) return fail(ctx, KMX_ERR_FORMAT, "text is not strict 4-line FASTQ");
-  return run_s1(ctx, d_text, nbytes, (const u32*)ctx->seq_start.p, (const u32*)ctx->seq_len.p, nrec, nbytes / 2);
+  CK(ensure(ln, ln->seq_start, nrec * 4));
+  CK(ensure(ln, ln->seq_len, nrec * 4));
+  CK(cudaMemsetAsync(ln->d_flags, 0, 8, ln->st));
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, ln->d_total,
+                     (u32*)ln->seq_start.p, (u32*)ln->seq_len.p, nrec, ln->d_flags, 1, ln->st, &ln->launches)); }
+  u32* fl = (u32*)ln->h_pin;
+  CK(cudaMemcpyAsync(fl, ln->d_flags, 8, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
+  if (fl[0]) return fail(ln, KMX_ERR_FORMAT, "text is not strict 4-line FASTQ");
+  return run_s1(ln, d_text, nbytes, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, nrec, nbytes / 2);
 }
 
-extern "C" int kmx_superk_push_reads(kmx_ctx* ctx, const char* seqs, const uint64_t* off, size_t nseq)
+static int superk_push_reads(Lane* ln, const char* seqs, const uint64_t* off, size_t nseq)
 {
-  if (!ctx || (nseq && (!seqs || !off))) return KMX_ERR_ARG;
-  if (!ctx->in_sample) return fail(ctx, KMX_ERR_STATE, "kmx_superk_push_reads outside begin/end");
+  if (!ln->in_sample) return fail(ln, KMX_ERR_STATE, "kmx_superk_push_reads outside begin/end");
   if (nseq == 0) return KMX_OK;
-  const u32 k = ctx->prm.kmer_size;
+  const u32 k = ln->ctx->prm.kmer_size;
   const u64 CH = 1024;                    // k-mers per segment for long sequences
-  // process in blocks of < 2 GiB of sequence
   size_t i = 0;
-  while (i < nseq) {
+  while (i < nseq) {                      // blocks of < 2 GiB of sequence
     u64 b0 = off[i];
     size_t j = i;
-    std::vector<u32> st, ln;
+    std::vector<u32> st, sl;
     u64 kmers = 0;
     while (j < nseq && off[j + 1] - b0 < 0x7FFFFFFFULL) {
       u64 s = off[j] - b0, len = off[j + 1] - off[j];
       if (len >= k) {
-        if (len <= CH + k - 1) { st.push_back((u32)s); ln.push_back((u32)len); }
-        else for (u64 c = 0; c + k <= len; c += CH) { st.push_back((u32)(s + c)); ln.push_back((u32)std::min<u64>(CH + k - 1, len - c)); }
+        if (len <= CH + k - 1) { st.push_back((u32)s); sl.push_back((u32)len); }
+        else for (u64 c = 0; c + k <= len; c += CH) { st.push_back((u32)(s + c)); sl.push_back((u32)std::min<u64>(CH + k - 1, len - c)); }
         kmers += len - k + 1;
       }
       j++;
     }
-    if (j == i) return fail(ctx, KMX_ERR_ARG, "sequence %zu is longer than 2 GiB", i);
+    if (j == i) return fail(ln, KMX_ERR_ARG, "sequence %zu is longer than 2 GiB", i);
     u64 nb = off[j] - b0;
     if (!st.empty()) {
-      CK(ensure(ctx, ctx->text, nb + 64));
-      CK(cudaMemcpyAsync(ctx->text.p, seqs + b0, nb, cudaMemcpyHostToDevice, ctx->st));
-      CK(ensure(ctx, ctx->seq_start, st.size() * 4));
-      CK(ensure(ctx, ctx->seq_len, st.size() * 4));
-      CK(cudaMemcpyAsync(ctx->seq_start.p, st.data(), st.size() * 4, cudaMemcpyHostToDevice, ctx->st));
-      CK(cudaMemcpyAsync(ctx->seq_len.p, ln.data(), ln.size() * 4, cudaMemcpyHostToDevice, ctx->st));
-      CK(cudaStreamSynchronize(ctx->st));
-      int rc = run_s1(ctx, (const uint8_t*)ctx->text.p, nb, (const u32*)ctx->seq_start.p, (const u32*)ctx->seq_len.p, st.size(), kmers);
+      CK(ensure(ln, ln->text, nb + 64));
+      CK(cudaMemcpyAsync(ln->text.p, seqs + b0, nb, cudaMemcpyHostToDevice, ln->st));
+      CK(ensure(ln, ln->seq_start, st.size() * 4));
+      CK(ensure(ln, ln->seq_len, st.size() * 4));
+      CK(cudaMemcpyAsync(ln->seq_start.p, st.data(), st.size() * 4, cudaMemcpyHostToDevice, ln->st));
+      CK(cudaMemcpyAsync(ln->seq_len.p, sl.data(), sl.size() * 4, cudaMemcpyHostToDevice, ln->st));
+      CK(cudaStreamSynchronize(ln->st));
+      int rc = run_s1(ln, (const uint8_t*)ln->text.p, nb, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, st.size(), kmers);
       if (rc) return rc;
     }
     i = j;
@@ -413,48 +481,60 @@ extern "C" int kmx_superk_push_reads(kmx_ctx* ctx, const char* seqs, const uint6
   return KMX_OK;
 }
 
-extern "C" int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition)
+static int superk_end(Lane* ln, uint64_t* kmers_per_partition)
 {
-  if (!ctx) return KMX_ERR_ARG;
-  if (!ctx->in_sample) return fail(ctx, KMX_ERR_STATE, "kmx_superk_end without begin");
-  if (kmers_per_partition) memcpy(kmers_per_partition, ctx->h_kcnt.data(), ctx->prm.nb_partitions * 8);
-  ctx->in_sample = false; ctx->sample_ready = true;
+  if (!ln->in_sample) return fail(ln, KMX_ERR_STATE, "kmx_superk_end without begin");
+  if (kmers_per_partition) memcpy(kmers_per_partition, ln->h_kcnt.data(), ln->ctx->prm.nb_partitions * 8);
+  ln->in_sample = false; ln->sample_ready = true;
   return KMX_OK;
 }
+
+extern "C" int kmx_superk_begin(kmx_ctx* ctx) { if (!ctx) return KMX_ERR_ARG; LANE0; return superk_begin(ln); }
+extern "C" int kmx_superk_push_fastq(kmx_ctx* ctx, const char* text, size_t nbytes, int on_device)
+{
+  if (!ctx || (!text && nbytes)) return KMX_ERR_ARG;
+  LANE0; return superk_push_fastq(ln, text, nbytes, on_device);
+}
+extern "C" int kmx_superk_push_reads(kmx_ctx* ctx, const char* seqs, const uint64_t* off, size_t nseq)
+{
+  if (!ctx || (nseq && (!seqs || !off))) return KMX_ERR_ARG;
+  LANE0; return superk_push_reads(ln, seqs, off, nseq);
+}
+extern "C" int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition) { if (!ctx) return KMX_ERR_ARG; LANE0; return superk_end(ln, kmers_per_partition); }
 
 // ---------------------------------------------------------------------------------------
 // stage 2
 // ---------------------------------------------------------------------------------------
-static int count_generic(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min);   // kmx_count_generic.cu part below
+static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min);
 
-static int count_hash_hist(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
+static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min)
 {
+  kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   const u64 Wb = ctx->prm.window_bits;
   const u32 S = (u32)((Wb + HIST_SUB - 1) / HIST_SUB);
   const size_t hist_bytes = (size_t)P * Wb * 4;
-  if (ctx->hist.cap < hist_bytes) {
-    CK(ensure(ctx, ctx->hist, hist_bytes));
-    CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->st));
+  if (ln->hist.cap < hist_bytes) {
+    CK(ensure(ln, ln->hist, hist_bytes));
+    CK(cudaMemsetAsync(ln->hist.p, 0, ln->hist.cap, ln->st));
   }
-  CK(ensure(ctx, ctx->sub_counts, (size_t)P * S * 4));
-  CK(ensure(ctx, ctx->sub_off, ((size_t)P * S + 1) * 8));
-  CK(cudaMemsetAsync(ctx->sub_counts.p, 0, (size_t)P * S * 4, ctx->st));
-  // bucket meta on device reflects the finished sample (cursor = records per partition)
-  S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ctx->records.p; c.boff = ctx->d_boff;
-  c.bcnt = ctx->d_cursor; c.max_bcnt = *std::max_element(ctx->h_cursor.begin(), ctx->h_cursor.end());
+  CK(ensure(ln, ln->sub_counts, (size_t)P * S * 4));
+  CK(ensure(ln, ln->sub_off, ((size_t)P * S + 1) * 8));
+  CK(ensure_pin(ln, ((size_t)P * S + 1) * 8 + (size_t)P * 32 + 256));
+  S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
+  c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   u64 mlo, mhi; fastmod_magic(Wb, mlo, mhi);
-  { PROF(KMX_PROF_HASH_HIST); CK(launch_hash_hist(c, Wb, Wb, mlo, mhi, (u32*)ctx->hist.p, hard_min, (u32*)ctx->sub_counts.p, S, ctx->st, &ctx->launches)); }
-  u64* so = (u64*)ctx->sub_off.p;
-  CK(launch_scan_u32((const u32*)ctx->sub_counts.p, so, (u64)P * S, so + (u64)P * S, ctx->st, &ctx->launches));
-  std::vector<u64> h_so((size_t)P * S + 1);
-  CK(cudaMemcpyAsync(h_so.data(), so, h_so.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
-  const u64 D = h_so.back();
+  { PROF(KMX_PROF_HASH_HIST); CK(launch_hash_hist(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, (u32*)ln->sub_counts.p, S, ln->st, &ln->launches)); }
+  u64* so = (u64*)ln->sub_off.p;
+  CK(launch_scan_u32((const u32*)ln->sub_counts.p, so, (u64)P * S, so + (u64)P * S, ln->st, &ln->launches));
+  u64* h_so = (u64*)ln->h_pin;
+  CK(cudaMemcpyAsync(h_so, so, ((size_t)P * S + 1) * 8, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
+  const u64 D = h_so[(size_t)P * S];
   void* kp = nullptr; void* cp = nullptr;
   CK(arena_alloc(ctx, D * 8, &kp));
   CK(arena_alloc(ctx, D * 4, &cp));
-  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ctx->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ctx->st, &ctx->launches)); }
+  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->st, &ln->launches)); }
   for (u32 p = 0; p < P; p++) {
     ListRef& L = ctx->lists[(size_t)sample * P + p];
     u64 b = h_so[(size_t)p * S], e = h_so[(size_t)(p + 1) * S];
@@ -463,18 +543,73 @@ static int count_hash_hist(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
   return KMX_OK;
 }
 
-extern "C" int kmx_count_sample(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min)
+static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
 {
-  if (!ctx) return KMX_ERR_ARG;
-  if (sample >= ctx->prm.nb_samples) return fail(ctx, KMX_ERR_ARG, "sample %u >= nb_samples", sample);
-  if (!ctx->sample_ready) return fail(ctx, KMX_ERR_STATE, "kmx_count_sample needs a sample finished by kmx_superk_end");
+  kmx_ctx* ctx = ln->ctx;
+  if (sample >= ctx->prm.nb_samples) return fail(ln, KMX_ERR_ARG, "sample %u >= nb_samples", sample);
+  if (!ln->sample_ready) return fail(ln, KMX_ERR_STATE, "kmx_count_sample needs a sample finished by kmx_superk_end");
   if (ctx->prm.key_kind == KMX_KEY_HASH) {
-    size_t free_b = 0, tot_b = 0;
-    CK(cudaMemGetInfo(&free_b, &tot_b));
     size_t hist_bytes = (size_t)ctx->prm.nb_partitions * ctx->prm.window_bits * 4;
-    if (ctx->hist.cap >= hist_bytes || hist_bytes < (free_b / 4)) return count_hash_hist(ctx, sample, hard_min);
+    int ok;
+    {
+      std::lock_guard<std::mutex> g(ctx->mu);
+      if (ctx->hist_ok < 0) {                      // decide once: histogram path if it fits comfortably
+        size_t free_b = 0, tot_b = 0;
+        cudaMemGetInfo(&free_b, &tot_b);
+        ctx->hist_ok = hist_bytes < (free_b / 8) ? 1 : 0;
+      }
+      ok = ctx->hist_ok;
+    }
+    if (ok == 1) return count_hash_hist(ln, sample, hard_min);
   }
-  return count_generic(ctx, sample, hard_min);
+  return count_generic(ln, sample, hard_min);
+}
+
+extern "C" int kmx_count_sample(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min) { if (!ctx) return KMX_ERR_ARG; LANE0; return count_sample(ln, sample, hard_min); }
+
+// ---- many samples, pipelined over lanes ---------------------------------------------------
+extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* texts, const size_t* nbytes, int on_device,
+                               const uint32_t* sample_ids, const uint32_t* hard_min, uint32_t nlanes,
+                               uint64_t* kmers_per_partition)
+{
+  if (!ctx || (n && (!texts || !nbytes || !hard_min))) return KMX_ERR_ARG;
+  if (n == 0) return KMX_OK;
+  if (nlanes < 1) nlanes = 1;
+  if (nlanes > 8) nlanes = 8;
+  if (nlanes > n) nlanes = n;
+  const u32 P = ctx->prm.nb_partitions;
+  cudaSetDevice(ctx->device);
+  while (ctx->lanes.size() < nlanes) { int rc = lane_create(ctx, (int)ctx->lanes.size()); if (rc) return rc; }
+  {                                                 // settle the hist/sort decision before threads start
+    Lane* ln = ctx->lanes[0].get();
+    if (ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok < 0) {
+      size_t free_b = 0, tot_b = 0;
+      CK(cudaMemGetInfo(&free_b, &tot_b));
+      size_t hist_bytes = (size_t)P * ctx->prm.window_bits * 4;
+      ctx->hist_ok = hist_bytes * nlanes < (free_b / 4) ? 1 : 0;
+    }
+  }
+  std::atomic<int> first_err(0);
+  auto work = [&](u32 t) {
+    cudaSetDevice(ctx->device);
+    Lane* ln = ctx->lanes[t].get();
+    for (u32 i = t; i < n && !first_err.load(); i += nlanes) {
+      const u32 sid = sample_ids ? sample_ids[i] : i;
+      int rc = superk_begin(ln);
+      if (!rc) rc = superk_push_fastq(ln, texts[i], nbytes[i], on_device);
+      if (!rc) rc = superk_end(ln, kmers_per_partition ? kmers_per_partition + (size_t)i * P : nullptr);
+      if (!rc) rc = count_sample(ln, sid, hard_min[i]);
+      if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); return; }
+    }
+    cudaStreamSynchronize(ln->st);
+  };
+  if (nlanes == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (u32 t = 0; t < nlanes; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  return first_err.load();
 }
 
 extern "C" int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n)
@@ -487,18 +622,21 @@ extern "C" int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition
 extern "C" int kmx_counts_get(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* keys, uint32_t* counts)
 {
   if (!ctx || sample >= ctx->prm.nb_samples || partition >= ctx->prm.nb_partitions) return KMX_ERR_ARG;
+  LANE0;
+  int rc = kmx_sync(ctx);                           // lists may have been produced on another lane
+  if (rc) return rc;
   const ListRef& L = ctx->lists[(size_t)sample * ctx->prm.nb_partitions + partition];
   if (L.n == 0) return KMX_OK;
   const bool two = (ctx->prm.key_kind == KMX_KEY_KMER && ctx->W == 2);
   if (keys) {
-    if (!two) CK(cudaMemcpyAsync(keys, L.lo, L.n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (!two) CK(cudaMemcpyAsync(keys, L.lo, L.n * 8, cudaMemcpyDeviceToHost, ln->st));
     else {
-      CK(cudaMemcpy2DAsync(keys, 16, L.lo, 8, 8, L.n, cudaMemcpyDeviceToHost, ctx->st));
-      CK(cudaMemcpy2DAsync(keys + 1, 16, L.hi, 8, 8, L.n, cudaMemcpyDeviceToHost, ctx->st));
+      CK(cudaMemcpy2DAsync(keys, 16, L.lo, 8, 8, L.n, cudaMemcpyDeviceToHost, ln->st));
+      CK(cudaMemcpy2DAsync(keys + 1, 16, L.hi, 8, 8, L.n, cudaMemcpyDeviceToHost, ln->st));
     }
   }
-  if (counts) CK(cudaMemcpyAsync(counts, L.cnt, L.n * 4, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  if (counts) CK(cudaMemcpyAsync(counts, L.cnt, L.n * 4, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 
@@ -506,6 +644,7 @@ extern "C" int kmx_counts_put(kmx_ctx* ctx, uint32_t sample, uint32_t partition,
                               const uint32_t* counts, uint64_t n)
 {
   if (!ctx || sample >= ctx->prm.nb_samples || partition >= ctx->prm.nb_partitions || (n && (!keys || !counts))) return KMX_ERR_ARG;
+  LANE0;
   ListRef& L = ctx->lists[(size_t)sample * ctx->prm.nb_partitions + partition];
   L = ListRef();
   if (n == 0) return KMX_OK;
@@ -513,14 +652,14 @@ extern "C" int kmx_counts_put(kmx_ctx* ctx, uint32_t sample, uint32_t partition,
   void* kp = nullptr; void* hp = nullptr; void* cp = nullptr;
   CK(arena_alloc(ctx, n * 8, &kp));
   CK(arena_alloc(ctx, n * 4, &cp));
-  if (!two) CK(cudaMemcpyAsync(kp, keys, n * 8, cudaMemcpyHostToDevice, ctx->st));
+  if (!two) CK(cudaMemcpyAsync(kp, keys, n * 8, cudaMemcpyHostToDevice, ln->st));
   else {
     CK(arena_alloc(ctx, n * 8, &hp));
-    CK(cudaMemcpy2DAsync(kp, 8, keys, 16, 8, n, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpy2DAsync(hp, 8, keys + 1, 16, 8, n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpy2DAsync(kp, 8, keys, 16, 8, n, cudaMemcpyHostToDevice, ln->st));
+    CK(cudaMemcpy2DAsync(hp, 8, keys + 1, 16, 8, n, cudaMemcpyHostToDevice, ln->st));
   }
-  CK(cudaMemcpyAsync(cp, counts, n * 4, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaMemcpyAsync(cp, counts, n * 4, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   L.lo = (u64*)kp; L.hi = (u64*)hp; L.cnt = (u32*)cp; L.n = n;
   return KMX_OK;
 }
@@ -528,31 +667,39 @@ extern "C" int kmx_counts_put(kmx_ctx* ctx, uint32_t sample, uint32_t partition,
 extern "C" int kmx_counts_vector(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint8_t* bits)
 {
   if (!ctx || !bits || sample >= ctx->prm.nb_samples || partition >= ctx->prm.nb_partitions) return KMX_ERR_ARG;
-  if (ctx->prm.key_kind != KMX_KEY_HASH) return fail(ctx, KMX_ERR_ARG, "kmx_counts_vector needs hash keys");
+  LANE0;
+  if (ctx->prm.key_kind != KMX_KEY_HASH) return fail(ln, KMX_ERR_ARG, "kmx_counts_vector needs hash keys");
+  int rc = kmx_sync(ctx);
+  if (rc) return rc;
   const u64 Wb = ctx->prm.window_bits;
   const ListRef& L = ctx->lists[(size_t)sample * ctx->prm.nb_partitions + partition];
-  CK(ensure(ctx, ctx->body, Wb / 8 + 8));
-  CK(cudaMemsetAsync(ctx->body.p, 0, Wb / 8 + 8, ctx->st));
-  CK(launch_hash_vector(L.lo, L.n, Wb * partition, (uint8_t*)ctx->body.p, ctx->st, &ctx->launches));
-  CK(cudaMemcpyAsync(bits, ctx->body.p, Wb / 8, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  CK(ensure(ln, ctx->body, Wb / 8 + 8));
+  CK(cudaMemsetAsync(ctx->body.p, 0, Wb / 8 + 8, ln->st));
+  CK(launch_hash_vector(L.lo, L.n, Wb * partition, (uint8_t*)ctx->body.p, ln->st, &ln->launches));
+  CK(cudaMemcpyAsync(bits, ctx->body.p, Wb / 8, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 
 // ---------------------------------------------------------------------------------------
 // stage 3 / 4
 // ---------------------------------------------------------------------------------------
-static int merge_sparse(kmx_ctx* ctx, uint32_t partition, const kmx_merge_params* mp, kmx_merge_result* res,
+static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp, kmx_merge_result* res,
                         const std::vector<MergeList>& hl, u64 max_n, u64 tot_n);
 
 extern "C" int kmx_merge_partition(kmx_ctx* ctx, uint32_t partition, const kmx_merge_params* mp, kmx_merge_result* res)
 {
   if (!ctx || !mp || !mp->soft_min || partition >= ctx->prm.nb_partitions) return KMX_ERR_ARG;
+  LANE0;
   const u32 N = ctx->prm.nb_samples, P = ctx->prm.nb_partitions;
   const bool hash = ctx->prm.key_kind == KMX_KEY_HASH;
-  if ((mp->format == KMX_FMT_BF || mp->format == KMX_FMT_BFT) && !hash) return fail(ctx, KMX_ERR_ARG, "bf/bft rows need hash keys");
-  if (mp->format > KMX_FMT_BFT) return fail(ctx, KMX_ERR_ARG, "bad format");
-  if (mp->emit_all && mp->format != KMX_FMT_COUNT) return fail(ctx, KMX_ERR_ARG, "emit_all needs KMX_FMT_COUNT");
+  if ((mp->format == KMX_FMT_BF || mp->format == KMX_FMT_BFT) && !hash) return fail(ln, KMX_ERR_ARG, "bf/bft rows need hash keys");
+  if (mp->format > KMX_FMT_BFT) return fail(ln, KMX_ERR_ARG, "bad format");
+  if (mp->emit_all && mp->format != KMX_FMT_COUNT) return fail(ln, KMX_ERR_ARG, "emit_all needs KMX_FMT_COUNT");
+  for (size_t i = 1; i < ctx->lanes.size(); i++) { Lane* o = ctx->lanes[i].get(); cudaError_t e = cudaStreamSynchronize(o->st); if (e != cudaSuccess) return fail(ln, KMX_ERR_CUDA, "lane sync: %s", cudaGetErrorString(e)); }
+  CK(ensure_pin(ln, N * sizeof(MergeList) + N * 4 + 256));
+  MergeList* hl_pin = (MergeList*)ln->h_pin;
+  u32* soft_pin = (u32*)(ln->h_pin + N * sizeof(MergeList));
   std::vector<MergeList> hl(N);
   u64 max_n = 0, tot_n = 0;
   for (u32 s = 0; s < N; s++) {
@@ -560,55 +707,53 @@ extern "C" int kmx_merge_partition(kmx_ctx* ctx, uint32_t partition, const kmx_m
     hl[s].lo = L.lo; hl[s].hi = L.hi; hl[s].cnt = L.cnt; hl[s].n = L.n;
     max_n = std::max(max_n, L.n); tot_n += L.n;
   }
-  CK(ensure(ctx, ctx->d_lists, N * sizeof(MergeList)));
-  CK(ensure(ctx, ctx->d_soft, N * 4));
-  CK(ensure(ctx, ctx->stats, (size_t)6 * N * 8));
-  CK(cudaMemcpyAsync(ctx->d_lists.p, hl.data(), N * sizeof(MergeList), cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemcpyAsync(ctx->d_soft.p, mp->soft_min, N * 4, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)6 * N * 8, ctx->st));
+  memcpy(hl_pin, hl.data(), N * sizeof(MergeList)); memcpy(soft_pin, mp->soft_min, N * 4);
+  CK(ensure(ln, ctx->d_lists, N * sizeof(MergeList)));
+  CK(ensure(ln, ctx->d_soft, N * 4));
+  CK(ensure(ln, ctx->stats, (size_t)6 * N * 8));
+  CK(cudaMemcpyAsync(ctx->d_lists.p, hl_pin, N * sizeof(MergeList), cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemcpyAsync(ctx->d_soft.p, soft_pin, N * 4, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)6 * N * 8, ln->st));
   ctx->last_emit_all = mp->emit_all;
-  if (mp->format == KMX_FMT_COUNT || mp->format == KMX_FMT_PA) {
-    int rc = merge_sparse(ctx, partition, mp, res, hl, max_n, tot_n);
-    // hl must outlive the async H2D copy above
-    cudaStreamSynchronize(ctx->st);
-    return rc;
-  }
+  if (mp->format == KMX_FMT_COUNT || mp->format == KMX_FMT_PA) return merge_sparse(ln, partition, mp, res, hl, max_n, tot_n);
   // dense Bloom slab
   const u64 Wb = ctx->prm.window_bits;
   const u32 rb = (N + 7) / 8;
   const size_t slab_bytes = (size_t)Wb * rb;
   uint8_t* slab = nullptr;
   if (ctx->merge_out && mp->format == KMX_FMT_BF) {
-    if (ctx->merge_out_cap < slab_bytes + 8) return fail(ctx, KMX_ERR_ARG, "merge output buffer too small (%zu < %zu)", ctx->merge_out_cap, slab_bytes + 8);
+    if (ctx->merge_out_cap < slab_bytes + 8) return fail(ln, KMX_ERR_ARG, "merge output buffer too small (%zu < %zu)", ctx->merge_out_cap, slab_bytes + 8);
     slab = (uint8_t*)ctx->merge_out;
-  } else { CK(ensure(ctx, ctx->body, slab_bytes + 8)); slab = (uint8_t*)ctx->body.p; }
-  { PROF(KMX_PROF_FILL); CK(cudaMemsetAsync(slab, 0, slab_bytes + 8, ctx->st)); }
+  } else { CK(ensure(ln, ctx->body, slab_bytes + 8)); slab = (uint8_t*)ctx->body.p; }
+  { PROF(KMX_PROF_FILL); CK(cudaMemsetAsync(slab, 0, slab_bytes + 8, ln->st)); }
   const bool need_si = mp->share_min != 0 || mp->recurrence_min > 1;
   u32* si = nullptr;
-  if (need_si) {
-    CK(ensure(ctx, ctx->solid_in, Wb * 4));
-    CK(cudaMemsetAsync(ctx->solid_in.p, 0, Wb * 4, ctx->st));
-    si = (u32*)ctx->solid_in.p;
-    { PROF(KMX_PROF_MERGE); CK(launch_dense_solid((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, Wb * partition, si, max_n, ctx->st, &ctx->launches)); }
+  {
+    PROF(KMX_PROF_MERGE);
+    if (need_si) {
+      CK(ensure(ln, ctx->solid_in, Wb * 4));
+      CK(cudaMemsetAsync(ctx->solid_in.p, 0, Wb * 4, ln->st));
+      si = (u32*)ctx->solid_in.p;
+      CK(launch_dense_solid((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, Wb * partition, si, max_n, ln->st, &ln->launches));
+    }
+    CK(launch_dense_emit((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, mp->recurrence_min, mp->share_min,
+                         Wb * partition, si, slab, rb, (u64*)ctx->stats.p, max_n, ln->st, &ln->launches));
   }
-  PROF(KMX_PROF_MERGE);
-  CK(launch_dense_emit((const MergeList*)ctx->d_lists.p, N, (const u32*)ctx->d_soft.p, mp->recurrence_min, mp->share_min,
-                       Wb * partition, si, slab, rb, (u64*)ctx->stats.p, max_n, ctx->st, &ctx->launches));
   ctx->last_body = slab;
   ctx->last_res.n_rows = Wb; ctx->last_res.row_bytes = rb; ctx->last_res.n_union = 0;
   if (mp->format == KMX_FMT_BFT) {
     // W x (8*rb) bits -> (8*rb) x W bits
-    CK(ensure(ctx, ctx->body2, slab_bytes + 8));
-    uint8_t* tout = (uint8_t*)ctx->body2.p;
+    uint8_t* tout;
     if (ctx->merge_out) {
-      if (ctx->merge_out_cap < slab_bytes + 8) return fail(ctx, KMX_ERR_ARG, "merge output buffer too small");
+      if (ctx->merge_out_cap < slab_bytes + 8) return fail(ln, KMX_ERR_ARG, "merge output buffer too small");
       tout = (uint8_t*)ctx->merge_out;
-    }
-    { PROF(KMX_PROF_TRANSPOSE); CK(launch_transpose_bits((const uint8_t*)ctx->body.p, Wb, (u64)rb * 8, tout, ctx->st, &ctx->launches)); }
+    } else { CK(ensure(ln, ctx->body2, slab_bytes + 8)); tout = (uint8_t*)ctx->body2.p; }
+    { PROF(KMX_PROF_TRANSPOSE); CK(launch_transpose_bits(slab, Wb, (u64)rb * 8, tout, ln->st, &ln->launches)); }
     ctx->last_body = tout;
     ctx->last_res.n_rows = (u64)rb * 8; ctx->last_res.row_bytes = Wb / 8;
   }
-  CK(cudaStreamSynchronize(ctx->st));     // hl / soft host buffers are released on return
+  // the pinned staging (lists, soft_min) is reused by the next merge: its H2D copies must be done.
+  CK(cudaStreamSynchronize(ln->st));
   if (res) *res = ctx->last_res;
   return KMX_OK;
 }
@@ -616,11 +761,12 @@ extern "C" int kmx_merge_partition(kmx_ctx* ctx, uint32_t partition, const kmx_m
 extern "C" int kmx_merge_get(kmx_ctx* ctx, void* body, uint64_t* stats, uint8_t* row_keep)
 {
   if (!ctx) return KMX_ERR_ARG;
+  LANE0;
   const u64 nb = ctx->last_res.n_rows * ctx->last_res.row_bytes;
-  if (body && nb) CK(cudaMemcpyAsync(body, ctx->last_body, nb, cudaMemcpyDeviceToHost, ctx->st));
-  if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, (size_t)6 * ctx->prm.nb_samples * 8, cudaMemcpyDeviceToHost, ctx->st));
-  if (row_keep && ctx->last_emit_all && ctx->last_res.n_rows) CK(cudaMemcpyAsync(row_keep, ctx->row_keep.p, ctx->last_res.n_rows, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  if (body && nb) CK(cudaMemcpyAsync(body, ctx->last_body, nb, cudaMemcpyDeviceToHost, ln->st));
+  if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, (size_t)6 * ctx->prm.nb_samples * 8, cudaMemcpyDeviceToHost, ln->st));
+  if (row_keep && ctx->last_emit_all && ctx->last_res.n_rows) CK(cudaMemcpyAsync(row_keep, ctx->row_keep.p, ctx->last_res.n_rows, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 
@@ -629,14 +775,15 @@ extern "C" const void* kmx_merge_body_device(kmx_ctx* ctx) { return ctx ? ctx->l
 extern "C" int kmx_transpose_bits(kmx_ctx* ctx, const uint8_t* in, uint64_t nrows, uint64_t ncols, uint8_t* out)
 {
   if (!ctx || !in || !out || (nrows % 8) || (ncols % 8)) return KMX_ERR_ARG;
+  LANE0;
   const size_t nb = (size_t)(nrows * ncols / 8);
   if (nb == 0) return KMX_OK;
-  CK(ensure(ctx, ctx->body, nb + 8));
-  CK(ensure(ctx, ctx->body2, nb + 8));
-  CK(cudaMemcpyAsync(ctx->body.p, in, nb, cudaMemcpyHostToDevice, ctx->st));
-  CK(launch_transpose_bits((const uint8_t*)ctx->body.p, nrows, ncols, (uint8_t*)ctx->body2.p, ctx->st, &ctx->launches));
-  CK(cudaMemcpyAsync(out, ctx->body2.p, nb, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  CK(ensure(ln, ctx->body, nb + 8));
+  CK(ensure(ln, ctx->body2, nb + 8));
+  CK(cudaMemcpyAsync(ctx->body.p, in, nb, cudaMemcpyHostToDevice, ln->st));
+  { PROF(KMX_PROF_TRANSPOSE); CK(launch_transpose_bits((const uint8_t*)ctx->body.p, nrows, ncols, (uint8_t*)ctx->body2.p, ln->st, &ln->launches)); }
+  CK(cudaMemcpyAsync(out, ctx->body2.p, nb, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 
@@ -647,14 +794,17 @@ extern "C" int kmx_synth_fastq(kmx_ctx* ctx, uint64_t seed, uint32_t sample, uin
                                uint32_t L, uint64_t G, double d, double e, int revcomp, char* dev_out)
 {
   if (!ctx || !dev_out || G < L) return KMX_ERR_ARG;
+  LANE0;
   auto thr = [](double p) { double v = p * 4294967296.0; return v >= 4294967295.0 ? 0xFFFFFFFFu : (u32)v; };
-  CK(launch_synth_fastq(seed, sample, first_read, R, L, G, thr(d), thr(e), revcomp, dev_out, ctx->st, &ctx->launches));
+  u64 dummy = 0;                                  // the generator is a test utility, not a hot-path launch
+  CK(launch_synth_fastq(seed, sample, first_read, R, L, G, thr(d), thr(e), revcomp, dev_out, ln->st, &dummy));
   return KMX_OK;
 }
 
 extern "C" int kmx_dev_alloc(kmx_ctx* ctx, size_t nbytes, void** dev_ptr)
 {
   if (!ctx || !dev_ptr) return KMX_ERR_ARG;
+  LANE0;
   CK(cudaMalloc(dev_ptr, nbytes ? nbytes : 1));
   ctx->user_allocs.push_back(*dev_ptr);
   return KMX_OK;
@@ -662,25 +812,29 @@ extern "C" int kmx_dev_alloc(kmx_ctx* ctx, size_t nbytes, void** dev_ptr)
 extern "C" int kmx_dev_free(kmx_ctx* ctx, void* dev_ptr)
 {
   if (!ctx) return KMX_ERR_ARG;
+  LANE0;
   auto it = std::find(ctx->user_allocs.begin(), ctx->user_allocs.end(), dev_ptr);
   if (it == ctx->user_allocs.end()) return KMX_ERR_ARG;
   ctx->user_allocs.erase(it);
-  CK(cudaStreamSynchronize(ctx->st));
+  int rc = kmx_sync(ctx);
+  if (rc) return rc;
   CK(cudaFree(dev_ptr));
   return KMX_OK;
 }
 extern "C" int kmx_memcpy_d2h(kmx_ctx* ctx, void* host, const void* dev, size_t nbytes)
 {
   if (!ctx) return KMX_ERR_ARG;
-  CK(cudaMemcpyAsync(host, dev, nbytes, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  LANE0;
+  CK(cudaMemcpyAsync(host, dev, nbytes, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 extern "C" int kmx_memcpy_h2d(kmx_ctx* ctx, void* dev, const void* host, size_t nbytes)
 {
   if (!ctx) return KMX_ERR_ARG;
-  CK(cudaMemcpyAsync(dev, host, nbytes, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  LANE0;
+  CK(cudaMemcpyAsync(dev, host, nbytes, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
   return KMX_OK;
 }
 extern "C" int kmx_host_alloc(size_t nbytes, void** host_ptr)

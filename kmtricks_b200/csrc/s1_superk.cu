@@ -113,20 +113,28 @@ fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
   u64 tile0 = (u64)blockIdx.x * FQ_TILE;
   // each thread owns 64 contiguous bytes here (blocked, so newline order == thread order)
   u64 off = tile0 + (u64)threadIdx.x * FQ_BYTES_PER_THREAD;
-  u32 wv[16];
+  u32 wm[16];                                  // per word: 0x80 at every byte that is a newline
   u32 cnt = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     u64 o = off + j * 16;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (o < nbytes_total) v = __ldg(base + o / 16);
-    wv[4 * j] = v.x; wv[4 * j + 1] = v.y; wv[4 * j + 2] = v.z; wv[4 * j + 3] = v.w;
-  }
+    u32 wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int b = 0; b < 64; b++) {
-    u64 pos = off + b;
-    u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-    if (pos >= lead && pos < nbytes_total && c == 0x0Au) cnt++;
+    for (int q = 0; q < 4; q++) {
+      u32 x = wv[q] ^ 0x0A0A0A0Au;
+      u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+      u32 msk = ~y & 0x80808080u;
+      // drop bytes outside [lead, nbytes_total)
+      u64 wpos = o + 4 * q;
+      if (wpos < lead || wpos + 4 > nbytes_total) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) { u64 pos = wpos + b; if (pos < lead || pos >= nbytes_total) msk &= ~(0x80u << (8 * b)); }
+      }
+      wm[4 * j + q] = msk;
+      cnt += __popc(msk);
+    }
   }
   u32 x = cnt;
   for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
@@ -136,11 +144,12 @@ fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
   for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s_warp[i];
   u64 g = tile_prefix[blockIdx.x] + wbase + x - cnt;
   if (cnt == 0) return;
-#pragma unroll 1
-  for (int b = 0; b < 64; b++) {
-    u64 pos = off + b;
-    u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-    if (pos >= lead && pos < nbytes_total && c == 0x0Au) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    u32 msk = wm[q];
+    while (msk) {
+      int bit = __ffs(msk) - 1; msk &= msk - 1;
+      u64 pos = off + 4 * q + (bit >> 3);
       u64 rec = g >> 2; u32 ph = (u32)(g & 3);
       u64 tpos = pos - lead;                       // position relative to text start
       if (rec < nrec) {

@@ -18,40 +18,94 @@
 namespace kmx {
 
 static constexpr int HH_THREADS = 256;
+static constexpr int HH_WARPS = HH_THREADS / 32;
 
-// grid: (x tiles, P).  One thread per record, loop over its k-mers.
+// grid: (x tiles, P).  Each warp takes 32 records at a time, stages them in shared memory with
+// the prefix sum of their k-mer counts, and then walks the k-mers of those records with all 32
+// lanes busy (lane t -> k-mer t, t+32, ...; the owning record is found by a 5-step binary
+// search in the warp's prefix array).  The histogram update is a fire-and-forget RED.
 template <int W>
 __global__ void __launch_bounds__(HH_THREADS)
 hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
-                 int k, u64 Wbits, FastMod64 fm, u32* __restrict__ hist, u32 hmin,
-                 u32* __restrict__ sub_counts, u32 S)
+                 int k, u64 Wbits, FastMod64 fm, u32* __restrict__ hist)
 {
+  __shared__ uint4 s_rec[HH_WARPS][32 * W];
+  __shared__ u32 s_pref[HH_WARPS][33];
   const u32 p = blockIdx.y;
   const u32 n = bcnt[p];
   const u64 b0 = boff[p];
+  const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   u32* __restrict__ h = hist + (u64)p * Wbits;
-  u32* __restrict__ sc = sub_counts + (u64)p * S;
-  for (u32 r = blockIdx.x * HH_THREADS + threadIdx.x; r < n; r += gridDim.x * HH_THREADS) {
-    if (W == 1) {
-      Rec1 rec = load_rec1(recs, b0 + r);
-      int nk = rec.n - k + 1;
-      for (int j = 0; j < nk; j++) {
-        u64 c; canon1(rec, k, j, c);
-        u64 key = fastmod64(xxh64_8(c), fm);
-        u32 old = atomicAdd(h + key, 1u);
-        if (old + 1u == hmin) atomicAdd(sc + (u32)(key / HIST_SUB), 1u);
-      }
-    } else {
-      Rec2 rec = load_rec2(recs, b0 + r);
-      int nk = rec.n - k + 1;
-      for (int j = 0; j < nk; j++) {
-        u64 clo, chi; canon2(rec, k, j, clo, chi);
-        u64 key = fastmod64(xxh64_16(clo, chi), fm);
-        u32 old = atomicAdd(h + key, 1u);
-        if (old + 1u == hmin) atomicAdd(sc + (u32)(key / HIST_SUB), 1u);
+  for (u32 r0 = (blockIdx.x * HH_WARPS + w) * 32; r0 < n; r0 += gridDim.x * HH_THREADS) {
+    const u32 r = r0 + lane;
+    u32 nk = 0;
+    if (r < n) {
+      if (W == 1) {
+        uint4 v = __ldg(recs + b0 + r);
+        s_rec[w][lane] = v;
+        nk = (v.w >> 24) - k + 1;
+      } else {
+        uint4 a = __ldg(recs + 2 * (b0 + r)), b = __ldg(recs + 2 * (b0 + r) + 1);
+        s_rec[w][2 * lane] = a; s_rec[w][2 * lane + 1] = b;
+        nk = (b.w >> 24) - k + 1;
       }
     }
+    u32 x = nk;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (u32)o) x += y; }
+    s_pref[w][lane + 1] = x;
+    if (lane == 0) s_pref[w][0] = 0;
+    const u32 T = __shfl_sync(0xffffffffu, x, 31);
+    __syncwarp();
+    for (u32 t = lane; t < T; t += 32) {
+      // largest q in [0,32) with pref[q] <= t
+      u32 q = 0;
+#pragma unroll
+      for (int st = 16; st > 0; st >>= 1) if (s_pref[w][q + st] <= t) q += st;
+      const int j = (int)(t - s_pref[w][q]);
+      u64 key;
+      if (W == 1) {
+        uint4 v = s_rec[w][q];
+        Rec1 rec; rec.lo = (u64)v.x | ((u64)v.y << 32);
+        u64 hh = (u64)v.z | ((u64)v.w << 32);
+        rec.n = (int)(hh >> 56); rec.hi = hh & 0x00FFFFFFFFFFFFFFULL;
+        u64 c; canon1(rec, k, j, c);
+        key = fastmod64(xxh64_8(c), fm);
+      } else {
+        uint4 a = s_rec[w][2 * q], b = s_rec[w][2 * q + 1];
+        Rec2 rec;
+        rec.v0 = (u64)a.x | ((u64)a.y << 32); rec.v1 = (u64)a.z | ((u64)a.w << 32);
+        rec.v2 = (u64)b.x | ((u64)b.y << 32);
+        u64 hh = (u64)b.z | ((u64)b.w << 32);
+        rec.n = (int)(hh >> 56); rec.v3 = hh & 0x00FFFFFFFFFFFFFFULL;
+        u64 clo, chi; canon2(rec, k, j, clo, chi);
+        key = fastmod64(xxh64_16(clo, chi), fm);
+      }
+      atomicAdd(h + key, 1u);       // result unused -> RED.ADD
+    }
+    __syncwarp();
   }
+}
+
+// survivors per 64K-slot sub-chunk: grid = P*S CTAs
+static constexpr int HC_THREADS = 256;
+__global__ void __launch_bounds__(HC_THREADS)
+hash_count_kernel(u64 Wbits, u32 S, const u32* __restrict__ hist, u32 hmin, u32* __restrict__ sub_counts)
+{
+  __shared__ u32 s_warp[HC_THREADS / 32];
+  const u32 p = blockIdx.x / S, s = blockIdx.x % S;
+  const u64 slot0 = (u64)s * HIST_SUB;
+  const u64 slot1 = min(Wbits, slot0 + HIST_SUB);
+  const uint4* __restrict__ h4 = reinterpret_cast<const uint4*>(hist + (u64)p * Wbits);
+  u32 c = 0;
+  for (u64 q = slot0 / 4 + threadIdx.x; q < slot1 / 4; q += HC_THREADS) {
+    uint4 v = h4[q];
+    c += (v.x >= hmin) + (v.y >= hmin) + (v.z >= hmin) + (v.w >= hmin);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_THREADS / 32; i++) t += s_warp[i]; sub_counts[blockIdx.x] = t; }
 }
 
 // grid = P*S CTAs; CTA (p, s) sweeps slots [s*HIST_SUB, min(W, (s+1)*HIST_SUB)) in order.
@@ -111,17 +165,18 @@ cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_ml
                              u32* hist, u32 hard_min, u32* sub_counts, u32 S,
                              cudaStream_t st, u64* launches)
 {
-  if (c.max_bcnt == 0) return cudaSuccess;
+  if (c.max_bcnt == 0) return cudaMemsetAsync(sub_counts, 0, (size_t)c.P * S * 4, st);
   FastMod64 fm; fm.d = mod_d; fm.mlo = mod_mlo; fm.mhi = mod_mhi;
   unsigned gx = (c.max_bcnt + HH_THREADS - 1) / HH_THREADS;
-  if (gx > 4096) gx = 4096;
+  if (gx > 592) gx = 592;                 // 4 waves of 148 SMs per partition row at most
   dim3 grid(gx, c.P);
   u32 hmin = hard_min ? hard_min : 1;
   if (c.W == 1)
-    hash_hist_kernel<1><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist, hmin, sub_counts, S);
+    hash_hist_kernel<1><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist);
   else
-    hash_hist_kernel<2><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist, hmin, sub_counts, S);
-  *launches += 1;
+    hash_hist_kernel<2><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist);
+  hash_count_kernel<<<c.P * S, HC_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_counts);
+  *launches += 2;
   return cudaGetLastError();
 }
 

@@ -1,0 +1,50 @@
+"""Host-side logic of the product package (no GPU): format writers, FASTX parser, synth."""
+import numpy as np
+
+from kmtricks_b200 import engine, formats, synth
+from oracle import oracle as O
+from tests.conftest import EDGE_FASTA, EDGE_FASTQ_CRLF
+
+
+def test_format_writers_match_oracle_encoders():
+    rng = np.random.default_rng(2)
+    n, N = 50, 11
+    lo = np.sort(rng.integers(0, 2**62, n, dtype=np.uint64)); hi = rng.integers(0, 2**60, n, dtype=np.uint64)
+    cnt = rng.integers(1, 1000, n, dtype=np.uint32)
+    assert formats.kmer_file(lo, cnt, 31, 3, 2) == O.enc_kmer_file(lo, hi, cnt, 31, 3, 2)
+    keys2 = np.stack([lo, hi], axis=1).reshape(-1)
+    assert formats.kmer_file(keys2, cnt, 63, 1, 0) == O.enc_kmer_file(lo, hi, cnt, 63, 1, 0)
+    big = np.sort(rng.integers(0, 2**40, 9000, dtype=np.uint64)); bc = rng.integers(1, 9, 9000, dtype=np.uint32)
+    assert formats.hash_file(big, bc, 0, 1) == O.enc_hash_file(big, bc, 0, 1)
+    counts = rng.integers(0, 3, (n, N), dtype=np.uint32)
+    body = np.zeros(n, dtype=[("k", "<u8"), ("c", "<u4", (N,))]); body["k"] = lo; body["c"] = counts
+    assert formats.matrix_header("count", "kmer", 31, N, 2) + body.tobytes() == O.enc_count_matrix(lo, hi, counts, 31, N)
+    assert formats.matrix_header("count", "hash", 31, N, 2) + body.tobytes() == O.enc_count_hash_matrix(lo, counts, N, 2)
+    pa = np.zeros(n, dtype=[("k", "<u8"), ("b", "u1", ((N + 7) // 8,))]); pa["k"] = lo; pa["b"] = O.pa_rows(counts)
+    assert formats.matrix_header("pa", "kmer", 31, N, 2) + pa.tobytes() == O.enc_pa_matrix(lo, hi, counts, 31, N)
+    assert formats.matrix_header("pa", "hash", 31, N, 2) + pa.tobytes() == O.enc_pa_hash_matrix(lo, counts, N, 2)
+    assert formats.matrix_header("bf", "hash", 31, N, 3, 640) == O.cmbf_header(N, 640, 3)
+    stats = rng.integers(0, 10**6, (6, N), dtype=np.uint64)
+    assert formats.merge_info(stats) == O.enc_merge_info(stats)
+    assert formats.hash_info(10**8, 4, 10) == O.enc_hash_info(10**8, 4, 10)
+    t = formats.static_repart_table(8, 13)
+    assert np.array_equal(t, O.repart_static(8, 13))
+    assert formats.minim_repart(t, 13) == O.enc_minim_repart(t, 13)
+    assert formats.read_minim_repart(formats.minim_repart(t, 13))[0] == 13
+    for bloom, P in ((10**8, 4), (2 * 10**8, 64), (1000, 3), (64, 1)):
+        assert formats.window_bits(bloom, P) == O.window_bits(bloom, P)
+
+
+def test_host_fastx_parser_matches_oracle_parser():
+    for buf in (EDGE_FASTA, EDGE_FASTQ_CRLF, b"", b">x\n", b">a\nAC\n>b\n\n>c\nGT", b"@q\nACGT\n+\nII\nII\n@r\nAA\n+\nII\n",
+                synth.make_fastq(1, 0, 20, L=40, G=500)):
+        assert engine.parse_fastx(buf) == O.fastx_parse(buf)
+
+
+def test_synth_is_deterministic_and_well_formed():
+    a = synth.make_fastq(9, 2, 100, L=80, G=5000, revcomp=True)
+    b = synth.make_fastq(9, 2, 60, L=80, G=5000, revcomp=True) + synth.make_fastq(9, 2, 40, L=80, G=5000, revcomp=True, first_read=60)
+    assert a == b
+    lines = a.split(b"\n")
+    assert len(lines) == 401 and lines[0] == b"@r00000000" and lines[2] == b"+" and set(lines[1]) <= set(b"ACGT")
+    assert len(a) == 100 * synth.record_bytes(80)

@@ -247,16 +247,23 @@ def main_kmx(args):
     # multi-GPU: samples shard over ranks (weak scaling: every rank parses `samples` samples)
     cfg = engine.Config(kmer_size=args.kmer_size, nb_partitions=args.partitions, mode=args.mode, hard_min=args.hard_min,
                         bloom_size=args.bloom_size)
-    N = args.samples
-    eng = engine.Engine(cfg, N, device=local)
+    N = args.samples                       # samples parsed by THIS rank (weak scaling)
+    N_tot = N * world                      # sample columns of every matrix
+    eng = engine.Engine(cfg, N_tot, device=local)
     L = eng.lib
     h = eng.h
+    if world > 1:
+        from kmtricks_b200 import dist as kd
+        kd.init_engine(eng, nlanes=args.lanes)
+        my_parts = list(kd.owned_partitions(args.partitions, world, rank))
+    else:
+        my_parts = list(range(args.partitions))
     rb = synth.record_bytes(args.read_len)
     sample_bytes = args.reads * rb
     kmers_step = n_kmers(args)
     P = args.partitions
     Wb = cfg.window_bits
-    row_bytes = (N + 7) // 8
+    row_bytes = (N_tot + 7) // 8
     slab_bytes = Wb * row_bytes
     fmt = cfg.fmt
 
@@ -273,8 +280,8 @@ def main_kmx(args):
     ck(L.kmx_sync(h), "sync")
     # all P bodies stay in HBM
     d_out = C.c_void_p()
-    ck(L.kmx_dev_alloc(h, P * (slab_bytes + 64) if fmt in ("bf", "bft") else 64, C.byref(d_out)), "dev_alloc out")
-    soft = np.full(N, cfg.soft_min, dtype=np.uint32)
+    ck(L.kmx_dev_alloc(h, len(my_parts) * (slab_bytes + 64) if fmt in ("bf", "bft") else 64, C.byref(d_out)), "dev_alloc out")
+    soft = np.full(N_tot, cfg.soft_min, dtype=np.uint32)
     mp = _lib.KmxMergeParams(soft.ctypes.data_as(C.POINTER(C.c_uint32)), cfg.recurrence_min, cfg.share_min,
                              {"count": 0, "pa": 1, "bf": 2, "bft": 3}[fmt], 0)
     res = _lib.KmxMergeResult()
@@ -292,18 +299,21 @@ def main_kmx(args):
     hmins = (C.c_uint32 * N)(*([args.hard_min] * N))
 
     def merges(to_host=None):
-        for p in range(P):
+        for j, p in enumerate(my_parts):
             if to_host is None and fmt in ("bf", "bft"):
-                tm("set_out", L.kmx_set_merge_output, h, d_out.value + p * (slab_bytes + 64), slab_bytes + 64)
+                tm("set_out", L.kmx_set_merge_output, h, d_out.value + j * (slab_bytes + 64), slab_bytes + 64)
             tm("merge", L.kmx_merge_partition, h, p, C.byref(mp), C.byref(res))
             if to_host is not None:
-                tm("merge_get", L.kmx_merge_get, h, to_host + p * slab_bytes, None, None)
+                tm("merge_get", L.kmx_merge_get, h, to_host + j * slab_bytes, None, None)
         tm("set_out", L.kmx_set_merge_output, h, None, 0)
 
     def make_step(ptrs, on_device, lanes, to_host=None):
         def step():
             tm("reset", L.kmx_reset, h)
-            tm("run_samples", L.kmx_run_samples, h, N, ptrs, sizes, on_device, None, hmins, lanes, None)
+            if world > 1:
+                tm("run_samples", L.kmx_dist_run_samples, h, N, ptrs, sizes, on_device, hmins, None)
+            else:
+                tm("run_samples", L.kmx_run_samples, h, N, ptrs, sizes, on_device, None, hmins, lanes, None)
             merges(to_host)
         return step
 
@@ -393,22 +403,35 @@ def main_kmx(args):
     e2e = None
     if not args.no_e2e:
         h_text = C.c_void_p(); h_out = C.c_void_p()
-        rc = L.kmx_host_alloc(N * sample_bytes, C.byref(h_text))
-        rc2 = L.kmx_host_alloc(max(P * slab_bytes, 64), C.byref(h_out))
+        # pinned staging for the FASTQ: all N samples if host RAM allows (all ranks share the box),
+        # otherwise the first K samples, cycled (same bytes moved, same stage-1/2 work)
+        K = N
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            budget = int(avail * 0.6) // max(world, 1) - len(my_parts) * slab_bytes
+            K = max(1, min(N, budget // sample_bytes))
+        except Exception:
+            pass
+        if world > 1:
+            t = torch.tensor([K], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN); K = int(t.item())
+        rc = L.kmx_host_alloc(K * sample_bytes, C.byref(h_text))
+        rc2 = L.kmx_host_alloc(max(len(my_parts) * slab_bytes, 64), C.byref(h_out))
         if rc or rc2:
             e2e = {"value": None, "unit": "k-mers/s", "error": "pinned host allocation failed"}
         else:
-            ck(L.kmx_memcpy_d2h(h, h_text, d_text, N * sample_bytes), "d2h text")
-            host_ptrs = (C.c_void_p * N)(*[h_text.value + s * sample_bytes for s in range(N)])
+            ck(L.kmx_memcpy_d2h(h, h_text, d_text, K * sample_bytes), "d2h text")
+            host_ptrs = (C.c_void_p * N)(*[h_text.value + (s % K) * sample_bytes for s in range(N)])
             step_host = make_step(host_ptrs, 0, args.lanes, to_host=h_out.value)
             step_host()
             ns = max(1, min(args.steps, 2))
             t0 = time.perf_counter()
             ms_e = timed(step_host, ns)
             wall_e = time.perf_counter() - t0
-            e2e = {"value": world * kmers_step / (ms_e / ns * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": N * sample_bytes,
-                   "d2h_bytes_per_step": P * slab_bytes, "ms_per_step": ms_e / ns, "wall_s_per_step": wall_e / ns,
-                   "what": "kmx_run_samples on pinned host FASTQ + kmx_merge_partition/kmx_merge_get into pinned host memory"}
+            e2e = {"value": world * kmers_step / (ms_e / ns * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": N * sample_bytes * world,
+                   "d2h_bytes_per_step": len(my_parts) * slab_bytes * world, "ms_per_step": ms_e / ns, "wall_s_per_step": wall_e / ns,
+                   "what": "kmx_run_samples on pinned host FASTQ + kmx_merge_partition/kmx_merge_get into pinned host memory",
+                   "host_text_samples": K}
             L.kmx_host_free(h_text); L.kmx_host_free(h_out)
 
     cpu = None
@@ -421,7 +444,8 @@ def main_kmx(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": f"cfg2: {N} samples x {args.reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
                                        f"P={P}, bloom={args.bloom_size}, hard-min {args.hard_min}, --static-repart, m=10"
-                                       + (f"; per GPU, {world} GPUs" if world > 1 else ""),
+                                       + (f"; samples per GPU (x{world} GPUs = {N_tot} columns), partitions sharded over GPUs, "
+                                          f"one NCCL all-to-all-v of bucket regions per sample" if world > 1 else ""),
                            "kmers_per_step": kmers_step, "l2": "inputs larger than L2 (315 MB text per launch)",
                            "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM", "lanes": args.lanes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

@@ -16,5 +16,5 @@ for f in s1_superk s2_hash s2_sort s3_merge s4_bits synth kmx_api; do
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT kmtricks_b200/_build/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT kmtricks_b200/_build/*.o -lcudart -ldl
 echo "built $OUT"

@@ -137,6 +137,21 @@ const void* kmx_merge_body_device(kmx_ctx* ctx);
  * nrows and ncols must be multiples of 8.  Host buffers.                                    */
 int kmx_transpose_bits(kmx_ctx* ctx, const uint8_t* in, uint64_t nrows, uint64_t ncols, uint8_t* out);
 
+/* ---- multi-GPU (one process per GPU) ----------------------------------------
+ * Stage 1 shards over samples, stages 2-4 over partitions: rank g owns the contiguous block
+ * [g*P/world, (g+1)*P/world).  kmx_dist_run_samples = kmx_run_samples + ONE exchange per
+ * sample: the bucket regions of every partition travel to the partition's owner (grouped
+ * ncclSend/ncclRecv over NVLink), who counts them.  Rank r's local sample i lands in slot
+ * r*n_local + i on every rank (for the partitions that rank owns), so nb_samples must be
+ * >= world*n_local.  Afterwards each rank merges its own partitions with kmx_merge_partition.
+ * Rendezvous: rank 0 draws `nlanes` ids with kmx_dist_unique_id, the host broadcasts them
+ * (torch.distributed / MPI / files), every rank calls kmx_dist_init with all of them.        */
+int kmx_dist_unique_id(uint8_t* out128);
+int kmx_dist_init(kmx_ctx* ctx, int rank, int world, uint32_t nlanes, const uint8_t* ids /* nlanes*128 */);
+int kmx_dist_owner(const kmx_ctx* ctx, uint32_t partition, int world);
+int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* const* texts, const size_t* nbytes, int on_device,
+                         const uint32_t* hard_min, uint64_t* kmers_per_partition);
+
 /* ---- utilities (benchmark / tests) ------------------------------------------------------ */
 /* device twin of kmtricks_b200/synth.py: writes R records of 2L+15 bytes to dev_out        */
 int kmx_synth_fastq(kmx_ctx* ctx, uint64_t seed, uint32_t sample, uint64_t first_read, uint64_t R,
@@ -154,7 +169,7 @@ int kmx_set_merge_output(kmx_ctx* ctx, void* dev_ptr, size_t cap_bytes);
 /* per-kernel-class device timing with CUDA events on the context's stream (bench roofline) */
 enum { KMX_PROF_INDEX = 0, KMX_PROF_S1 = 1, KMX_PROF_HASH_HIST = 2, KMX_PROF_HASH_EMIT = 3, KMX_PROF_EXPAND = 4,
        KMX_PROF_SORT = 5, KMX_PROF_RLE = 6, KMX_PROF_MERGE = 7, KMX_PROF_TRANSPOSE = 8, KMX_PROF_FILL = 9,
-       KMX_PROF_KINDS = 10 };
+       KMX_PROF_EXCHANGE = 10, KMX_PROF_KINDS = 11 };
 int kmx_profile_enable(kmx_ctx* ctx, int on);
 int kmx_profile_reset(kmx_ctx* ctx);
 int kmx_profile_get(kmx_ctx* ctx, int kind, double* total_ms, uint64_t* count);

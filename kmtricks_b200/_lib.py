@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libkmx_sm100.so")
 KMX_OK, KMX_ERR_ARG, KMX_ERR_CUDA, KMX_ERR_FORMAT, KMX_ERR_NOMEM, KMX_ERR_STATE = range(6)
 KEY_KMER, KEY_HASH = 0, 1
 FMT_COUNT, FMT_PA, FMT_BF, FMT_BFT = 0, 1, 2, 3
-PROF_KINDS = ["fq_index", "s1_superk", "hash_hist", "hash_emit", "expand", "radix_sort", "rle", "merge", "transpose", "fill"]
+PROF_KINDS = ["fq_index", "s1_superk", "hash_hist", "hash_emit", "expand", "radix_sort", "rle", "merge", "transpose", "fill", "exchange"]
 
 
 class KmxParams(C.Structure):
@@ -44,6 +44,10 @@ SYMBOLS = {
     "kmx_superk_end": (_i, [_vp, C.POINTER(_u64)]),
     "kmx_count_sample": (_i, [_vp, _u32, _u32]),
     "kmx_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u32), _u32, C.POINTER(_u64)]),
+    "kmx_dist_unique_id": (_i, [_vp]),
+    "kmx_dist_init": (_i, [_vp, _i, _i, _u32, _vp]),
+    "kmx_dist_owner": (_i, [_vp, _u32, _i]),
+    "kmx_dist_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u64)]),
     "kmx_counts_size": (_i, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "kmx_counts_get": (_i, [_vp, _u32, _u32, _vp, _vp]),
     "kmx_counts_put": (_i, [_vp, _u32, _u32, _vp, _vp, _u64]),

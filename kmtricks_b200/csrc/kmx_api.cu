@@ -50,6 +50,7 @@ struct ProfSpan { cudaEvent_t a, b; int kind; };
 }  // namespace
 
 struct kmx_ctx;
+struct KmxDist;
 
 // A lane owns everything one in-flight sample needs (stream, text staging, line index, bucket
 // slab, histogram, sort scratch).  Lane 0 also serves the single-sample API and the merges;
@@ -100,6 +101,7 @@ struct kmx_ctx {
   kmx_merge_result last_res{};
   u32 last_emit_all = 0;
   uint8_t* last_body = nullptr;    // where the final body lives
+  std::shared_ptr<KmxDist> dist;   // multi-GPU state (kmx_dist.inl)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -269,10 +271,14 @@ extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
   return KMX_OK;
 }
 
+static void dist_destroy(kmx_ctx* ctx);
+
 extern "C" void kmx_destroy(kmx_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (auto& lp : ctx->lanes) if (lp->st) cudaStreamSynchronize(lp->st);
+  dist_destroy(ctx);
   for (auto& lp : ctx->lanes) lane_destroy(lp.get());
   DBuf* bufs[] = {&ctx->d_lists, &ctx->d_soft, &ctx->solid_in, &ctx->body, &ctx->body2, &ctx->stats, &ctx->keep, &ctx->out_row,
                   &ctx->row_keep, &ctx->uni_lo, &ctx->uni_hi, &ctx->uni_lo2, &ctx->uni_hi2, &ctx->scan_work};
@@ -875,3 +881,4 @@ extern "C" int kmx_profile_get(kmx_ctx* ctx, int kind, double* total_ms, uint64_
 }
 
 #include "kmx_generic.inl"
+#include "kmx_dist.inl"

@@ -251,7 +251,7 @@ extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
   ctx->W = (k + 31) / 32;
   ctx->wlen = (int)(k - m + 1);
   ctx->max_nk = (ctx->W == 1 ? KMX_REC1_MAXN : KMX_REC2_MAXN) - (int)k + 1;
-  if (s1_smem_bytes(ctx->W, 2048, ctx->wlen, prm->nb_partitions) > 200 * 1024)
+  if (s1_smem_bytes(128, 2048, ctx->wlen, prm->nb_partitions) > 200 * 1024)
     return fail(ln, KMX_ERR_ARG, "nb_partitions %u too large for the stage-1 staging layout", prm->nb_partitions);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -380,8 +380,9 @@ static int superk_begin(Lane* ln)
 
 // run stage 1 over nseg segments described by (d_start, d_len) into the buckets; retries
 // with exact capacities when a bucket overflowed.
-static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers)
+static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers, u32 max_len)
 {
+  if (max_len > 2048) return fail(ln, KMX_ERR_FORMAT, "sequence of %u bases: stage 1 takes segments of <= 2048 bases (kmx_superk_push_reads splits long sequences)", max_len);
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   // optimistic capacity: ~1 record per 8 k-mers, 30% head-room for partition imbalance
@@ -398,6 +399,7 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
     a.k = (int)ctx->prm.kmer_size; a.m = (int)ctx->prm.minim_size; a.wlen = ctx->wlen; a.max_nk = ctx->max_nk;
     a.P = P; a.repart = ctx->d_repart; a.records = ln->records.p; a.boff = ln->d_boff; a.bcap = ln->d_bcap;
     a.cursor = ln->d_cursor; a.kcnt = ln->d_kcnt; a.overflow = ln->d_flags + 2;
+    a.pack_words = (max_len + 15) / 16; if (a.pack_words < 1) a.pack_words = 1;
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
     { PROF(KMX_PROF_S1); CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
     u64* kc = (u64*)ln->h_pin; u32* cur = (u32*)(ln->h_pin + P * 8); u32* ovf = (u32*)(ln->h_pin + P * 12);
@@ -445,7 +447,7 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   CK(cudaMemcpyAsync(fl, ln->d_flags, 8, cudaMemcpyDeviceToHost, ln->st));
   CK(cudaStreamSynchronize(ln->st));
   if (fl[0]) return fail(ln, KMX_ERR_FORMAT, "text is not strict 4-line FASTQ");
-  return run_s1(ln, d_text, nbytes, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, nrec, nbytes / 2);
+  return run_s1(ln, d_text, nbytes, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, nrec, nbytes / 2, fl[1]);
 }
 
 static int superk_push_reads(Lane* ln, const char* seqs, const uint64_t* off, size_t nseq)
@@ -479,7 +481,8 @@ static int superk_push_reads(Lane* ln, const char* seqs, const uint64_t* off, si
       CK(cudaMemcpyAsync(ln->seq_start.p, st.data(), st.size() * 4, cudaMemcpyHostToDevice, ln->st));
       CK(cudaMemcpyAsync(ln->seq_len.p, sl.data(), sl.size() * 4, cudaMemcpyHostToDevice, ln->st));
       CK(cudaStreamSynchronize(ln->st));
-      int rc = run_s1(ln, (const uint8_t*)ln->text.p, nb, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, st.size(), kmers);
+      u32 mx = 0; for (u32 v : sl) mx = std::max(mx, v);
+      int rc = run_s1(ln, (const uint8_t*)ln->text.p, nb, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, st.size(), kmers, mx);
       if (rc) return rc;
     }
     i = j;

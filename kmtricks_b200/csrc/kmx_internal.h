@@ -27,10 +27,11 @@ struct S1Args {
   u32* cursor;                  // [P] records appended (may exceed bcap -> overflow)
   u64* kcnt;                    // [P] k-mers appended
   u32* overflow;                // set when a record did not fit
-  u32 stage_cap;                // staging capacity (records)
+  u32 pack_words;               // 32-bit words of packed bases kept per segment = ceil(max segment length / 16)
+  u32 stage_cap;                // staging capacity (cut events)
   u32 flush_thr;                // flush when staged > flush_thr
 };
-size_t s1_smem_bytes(int W, u32 stage_cap, int wlen, u32 P);
+size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P);
 u64 fq_num_tiles(const uint8_t* text, u64 nbytes);
 cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
                             u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,

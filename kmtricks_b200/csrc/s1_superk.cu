@@ -188,35 +188,56 @@ __global__ void fq_fix_len(const uint8_t* __restrict__ text, const u32* __restri
 // ------------------------------------------------------------------------------------
 // main stage-1 kernel
 // ------------------------------------------------------------------------------------
+// One thread per sequence segment streams its bases 8 at a time:
+//   * 2-bit code + validity from the character (code = (c>>1)&3; valid <=> "ACTG"[code] == c&0xDF)
+//   * rolling forward / reverse-complement m-mer, lut value computed arithmetically
+//   * sliding minimum over the k-m+1 m-mers: block prefix / suffix-min ring in shared memory
+//     (all threads of the CTA are at the same base index, so the ring index is uniform)
+//   * the bases are also packed 16 per word (big-endian) into shared memory
+//   * a super-k-mer CUT only logs an 6-byte event (thread, start, #k-mers, partition) -- the
+//     divergent path is ~8 instructions
+// Every few rounds the CTA flushes cooperatively: per-partition counting in shared memory, ONE
+// global atomic per (flush, partition), then every event is turned into a 16/32-byte record by
+// funnel-shifting the packed bases (dense loop, no divergence) and stored to the bucket slab.
 template <int W> struct RecT;
 template <> struct RecT<1> { typedef uint4 type; };
 template <> struct RecT<2> { struct __align__(16) type { uint4 a, b; }; };
 
-
-
 static constexpr int S1_THREADS = 128;
 static constexpr int S1_ROUND = 8;
+
+// bits [32*jw, 32*jw+32) of (X >> s), X = big-endian words S(0..nwords) of thread t's packed read
+__device__ __forceinline__ u32 pack_word(const u32* __restrict__ s_pack, u32 t, int nwords, int top_word, int s, int jw)
+{
+  // X is the (top_word+1)-word big-endian number ending at word `top_word`; LSB word index 0 == top_word
+  int q = s + 32 * jw;
+  int wi = q >> 5, sh = q & 31;
+  int a = top_word - wi, b = a - 1;               // b is the more significant neighbour
+  u32 xa = (a >= 0 && a < nwords) ? s_pack[a * S1_THREADS + t] : 0u;
+  u32 xb = (b >= 0 && b < nwords) ? s_pack[b * S1_THREADS + t] : 0u;
+  return __funnelshift_r(xa, xb, sh);
+}
 
 template <int W>
 __global__ void __launch_bounds__(S1_THREADS)
 s1_superk(const S1Args a)
 {
-  typedef typename RecT<W>::type Rec;
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: recs[stage_cap] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | part[stage_cap] | rank[stage_cap]
-  Rec* s_rec = reinterpret_cast<Rec*>(smem);
-  u32* s_ring = reinterpret_cast<u32*>(s_rec + a.stage_cap);
+  // layout: pack[pack_words*128] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | ev[cap] | evp[cap] | rank[cap]
+  u32* s_pack = reinterpret_cast<u32*>(smem);
+  u32* s_ring = s_pack + a.pack_words * S1_THREADS;
   u32* s_hist = s_ring + a.wlen * S1_THREADS;
   u32* s_gbase = s_hist + a.P;
   u32* s_kc = s_gbase + a.P;
-  uint16_t* s_part = reinterpret_cast<uint16_t*>(s_kc + a.P);
-  uint16_t* s_rank = s_part + a.stage_cap;
+  u32* s_ev = s_kc + a.P;
+  uint16_t* s_evp = reinterpret_cast<uint16_t*>(s_ev + a.stage_cap);
+  uint16_t* s_rank = s_evp + a.stage_cap;
   __shared__ u32 s_count;
   __shared__ u32 s_maxlen;
 
-  const int tid = threadIdx.x;
+  const u32 tid = threadIdx.x;
   const int k = a.k, m = a.m, wlen = a.wlen;
-  const u32 mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+  const u32 mmask = (1u << (2 * m)) - 1u;
   const u32 ban_mask = 0x55555555u & ((1u << (2 * (m - 2))) - 1u);
   const int rsh = 2 * (m - 1);
 
@@ -237,65 +258,51 @@ s1_superk(const S1Args a)
   __syncthreads();
   const u32 maxlen = s_maxlen;
 
-  // char reader: aligned 8-byte words
+  // character reader: aligned 32-bit words + funnel shift
   const uint8_t* addr = a.text + start;
-  const u64* wp = reinterpret_cast<const u64*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)7);
-  int bi = (int)(reinterpret_cast<uintptr_t>(addr) & 7);
-  const u64* wend = reinterpret_cast<const u64*>((reinterpret_cast<uintptr_t>(a.text) + a.text_bytes + 7) & ~(uintptr_t)7);
-  u64 wcur = (len && wp < wend) ? __ldg(wp) : 0;
+  const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+  const u32 csh = 8u * (u32)(reinterpret_cast<uintptr_t>(addr) & 3);
+  const u32* wend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(a.text) + a.text_bytes + 3) & ~(uintptr_t)3);
+  u32 wprev = (len && wp < wend) ? __ldg(wp) : 0u;
 
   u32 fm = 0, rm = 0;                 // rolling forward / revcomp m-mer
-  u64 acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // shift register of recent bases (acc0 lowest)
+  u32 pk = 0;                         // packed bases of the current 16-base word
   int bad = 0;                        // >0 : k-mer ending here is invalid
   u32 nk = 0;                         // k-mers in the open record
   u32 cur_min = 0, cur_p = 0;
   u32 pre = 0xFFFFFFFFu;
   int j = 0;                          // m-mer index mod wlen (uniform)
 
-  auto flush_record = [&]() {
-    // open record holds the last n = k + nk - 1 bases of acc
-    u32 n = (u32)k + nk - 1;
+  auto log_cut = [&](u32 end_excl) {
+    // the open record covers bases [end_excl - (k+nk-1), end_excl)
     u32 slot = atomicAdd(&s_count, 1u);
-    if (W == 1) {
-      u64 lo = acc0, hi = acc1;
-      if (n < 32) { lo &= ((1ULL << (2 * n)) - 1ULL); hi = 0; }
-      else if (n < 64) { hi &= ((1ULL << (2 * (n - 32))) - 1ULL); }
-      hi |= (u64)n << 56;
-      uint4 r; r.x = (u32)lo; r.y = (u32)(lo >> 32); r.z = (u32)hi; r.w = (u32)(hi >> 32);
-      reinterpret_cast<uint4*>(s_rec)[slot] = r;
-    } else {
-      u64 v0 = acc0, v1 = acc1, v2 = acc2, v3 = acc3;
-      // mask to 2n bits, n <= 124
-      u32 bits = 2 * n;
-      if (bits < 64) { v0 &= ((1ULL << bits) - 1ULL); v1 = v2 = v3 = 0; }
-      else if (bits < 128) { if (bits > 64) v1 &= ((1ULL << (bits - 64)) - 1ULL); else v1 = 0; v2 = v3 = 0; }
-      else if (bits < 192) { if (bits > 128) v2 &= ((1ULL << (bits - 128)) - 1ULL); else v2 = 0; v3 = 0; }
-      else { if (bits > 192) v3 &= ((1ULL << (bits - 192)) - 1ULL); else v3 = 0; }
-      v3 |= (u64)n << 56;
-      uint4* dst = reinterpret_cast<uint4*>(s_rec) + 2 * slot;
-      uint4 r0, r1;
-      r0.x = (u32)v0; r0.y = (u32)(v0 >> 32); r0.z = (u32)v1; r0.w = (u32)(v1 >> 32);
-      r1.x = (u32)v2; r1.y = (u32)(v2 >> 32); r1.z = (u32)v3; r1.w = (u32)(v3 >> 32);
-      dst[0] = r0; dst[1] = r1;
-    }
-    s_part[slot] = (uint16_t)cur_p;
-    s_rank[slot] = (uint16_t)nk;          // nk parked here until the flush computes ranks
+    s_ev[slot] = tid | ((end_excl - (u32)k - nk + 1u) << 7) | (nk << 18);
+    s_evp[slot] = (uint16_t)cur_p;
     nk = 0;
   };
 
   for (u32 i0 = 0; i0 < maxlen; i0 += S1_ROUND) {
-#pragma unroll 1
+    // fetch the 8 characters of this round (2 words)
+    u32 c4[2] = {0u, 0u};
+    if (i0 < len) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        ++wp;
+        u32 wn = (wp < wend) ? __ldg(wp) : 0u;
+        c4[q] = __funnelshift_r(wprev, wn, csh);
+        wprev = wn;
+      }
+    }
+#pragma unroll
     for (u32 ii = 0; ii < S1_ROUND; ii++) {
       const u32 i = i0 + ii;
       const bool active = i < len;
-      u32 c = 0; bool valid = false;
-      if (active) {
-        u32 ch = (u32)(wcur >> (8 * bi)) & 0xFFu;
-        if (++bi == 8) { bi = 0; ++wp; wcur = (wp < wend) ? __ldg(wp) : 0; }
-        c = nt_code(ch); valid = nt_valid(ch);
-      }
+      const u32 ch = (c4[ii >> 2] >> (8 * (ii & 3))) & 0xFFu;
+      const u32 c = (ch >> 1) & 3u;
+      const bool valid = active && (((0x47544341u >> (8 * c)) & 0xFFu) == (ch & 0xDFu));   // "ACTG"[c]
       fm = ((fm << 2) | c) & mmask;
       rm = (rm >> 2) | ((c ^ 2u) << rsh);
+      pk = (pk << 2) | c;
       bad = valid ? max(bad - 1, 0) : k;
       u32 wmin = 0xFFFFFFFFu;
       if (i + 1 >= (u32)m) {                           // uniform
@@ -318,26 +325,26 @@ s1_superk(const S1Args a)
       }
       if (active) {
         const bool kvalid = (i + 1 >= (u32)k) && (bad == 0);
-        if (nk && (!kvalid || wmin != cur_min || nk == (u32)a.max_nk)) flush_record();
-        // shift the base in
-        if (W == 2) { acc3 = (acc3 << 2) | (acc2 >> 62); acc2 = (acc2 << 2) | (acc1 >> 62); }
-        acc1 = (acc1 << 2) | (acc0 >> 62);
-        acc0 = (acc0 << 2) | c;
+        if (nk && (!kvalid || wmin != cur_min || nk == (u32)a.max_nk)) log_cut(i);
         if (kvalid) {
           if (nk == 0) { cur_min = wmin; cur_p = __ldg(a.repart + wmin); }
           nk++;
         }
-        if (i + 1 == len && nk) flush_record();
+        if (i + 1 == len) {
+          if (nk) log_cut(i + 1);
+          if ((i & 7u) != 7u) s_pack[(i >> 4) * S1_THREADS + tid] = pk << (2u * (15u - (i & 15u)));   // partial last word
+        }
       }
     }
+    // bases [i0, i0+8) are complete for every active thread: publish the (half) word
+    if (i0 + 7 < len) s_pack[(i0 >> 4) * S1_THREADS + tid] = (i0 & 8u) ? pk : (pk << 16);
     __syncthreads();
     if (s_count > a.flush_thr || i0 + S1_ROUND >= maxlen) {
       const u32 n = s_count;
       for (u32 r = tid; r < n; r += S1_THREADS) {
-        u32 p = s_part[r];
-        u32 nkr = s_rank[r];
+        u32 p = s_evp[r];
         s_rank[r] = (uint16_t)atomicAdd(&s_hist[p], 1u);
-        atomicAdd(&s_kc[p], nkr);
+        atomicAdd(&s_kc[p], (s_ev[r] >> 18) & 127u);
       }
       __syncthreads();
       for (u32 p = tid; p < a.P; p += S1_THREADS) {
@@ -349,12 +356,48 @@ s1_superk(const S1Args a)
         }
       }
       __syncthreads();
-      Rec* out = reinterpret_cast<Rec*>(a.records);
+      uint4* out = reinterpret_cast<uint4*>(a.records);
       for (u32 r = tid; r < n; r += S1_THREADS) {
-        u32 p = s_part[r];
-        u32 pos = s_gbase[p] + s_rank[r];
-        if (pos < a.bcap[p]) out[a.boff[p] + pos] = s_rec[r];
-        else *a.overflow = 1u;
+        const u32 ev = s_ev[r], p = s_evp[r];
+        const u32 t = ev & 127u, st = (ev >> 7) & 2047u, nkr = (ev >> 18) & 127u;
+        const u32 nb = (u32)k + nkr - 1u;                     // bases in the record
+        const u32 pos = s_gbase[p] + s_rank[r];
+        // V = bases [st, st+nb) as a big number: X >> s with X ending at word `top`
+        const int top = (int)((st + nb - 1u) >> 4);
+        const int s = 2 * (int)(15u - ((st + nb - 1u) & 15u));
+        if (W == 1) {
+          u32 v[4];
+#pragma unroll
+          for (int jw = 0; jw < 4; jw++) v[jw] = pack_word(s_pack, t, a.pack_words, top, s, jw);
+          // mask to 2*nb bits (nb <= 60), put nb in the top byte
+          const u32 bits = 2u * nb;
+#pragma unroll
+          for (int jw = 0; jw < 4; jw++) {
+            const int lo = 32 * jw;
+            if ((int)bits <= lo) v[jw] = 0u;
+            else if ((int)bits < lo + 32) v[jw] &= (1u << (bits - lo)) - 1u;
+          }
+          v[3] |= nb << 24;
+          if (pos < a.bcap[p]) out[a.boff[p] + pos] = make_uint4(v[0], v[1], v[2], v[3]);
+          else *a.overflow = 1u;
+        } else {
+          u32 v[8];
+#pragma unroll
+          for (int jw = 0; jw < 8; jw++) v[jw] = pack_word(s_pack, t, a.pack_words, top, s, jw);
+          const u32 bits = 2u * nb;
+#pragma unroll
+          for (int jw = 0; jw < 8; jw++) {
+            const int lo = 32 * jw;
+            if ((int)bits <= lo) v[jw] = 0u;
+            else if ((int)bits < lo + 32) v[jw] &= (1u << (bits - lo)) - 1u;
+          }
+          v[7] |= nb << 24;
+          if (pos < a.bcap[p]) {
+            uint4* dst = out + 2 * (a.boff[p] + pos);
+            dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+          } else *a.overflow = 1u;
+        }
       }
       __syncthreads();
       if (tid == 0) s_count = 0;
@@ -366,10 +409,9 @@ s1_superk(const S1Args a)
 // ------------------------------------------------------------------------------------
 // host-side launchers (called from kmx_api.cu)
 // ------------------------------------------------------------------------------------
-size_t s1_smem_bytes(int W, u32 stage_cap, int wlen, u32 P)
+size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P)
 {
-  size_t rec = (W == 1) ? 16 : 32;
-  return (size_t)stage_cap * rec + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)stage_cap * 4;
+  return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)stage_cap * 8;
 }
 
 cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
@@ -408,7 +450,7 @@ u64 fq_num_tiles(const uint8_t* text, u64 nbytes)
 cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches)
 {
   if (a.nseg == 0) return cudaSuccess;
-  size_t smem = s1_smem_bytes(W, a.stage_cap, a.wlen, a.P);
+  size_t smem = s1_smem_bytes(a.pack_words, a.stage_cap, a.wlen, a.P);
   unsigned grid = (unsigned)((a.nseg + S1_THREADS - 1) / S1_THREADS);
   cudaError_t e;
   if (W == 1) {

@@ -218,32 +218,48 @@ __device__ __forceinline__ u32 pack_word(const u32* __restrict__ s_pack, u32 t, 
   return __funnelshift_r(xa, xb, sh);
 }
 
+// suffix-min rebuild of one thread's ring column when a block of wlen m-mers is complete
+__device__ __noinline__ void ring_suffix_min(u32* __restrict__ col, int wlen)
+{
+  u32 accm = 0xFFFFFFFFu;
+  for (int t2 = wlen - 1; t2 >= 0; t2--) {
+    accm = min(accm, col[t2 * S1_THREADS]);
+    col[t2 * S1_THREADS] = accm;
+  }
+}
+
+static constexpr u32 S1_EVW = 512;        // cut events per warp queue
+static constexpr u32 S1_EVTHR = 512 - 32 * 9;
+
 template <int W>
 __global__ void __launch_bounds__(S1_THREADS)
 s1_superk(const S1Args a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: pack[pack_words*128] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | ev[cap] | evp[cap] | rank[cap]
+  // layout: pack[pack_words*128] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | ev[4*512] | evp[4*512] | rank[4*512]
   u32* s_pack = reinterpret_cast<u32*>(smem);
   u32* s_ring = s_pack + a.pack_words * S1_THREADS;
   u32* s_hist = s_ring + a.wlen * S1_THREADS;
   u32* s_gbase = s_hist + a.P;
   u32* s_kc = s_gbase + a.P;
   u32* s_ev = s_kc + a.P;
-  uint16_t* s_evp = reinterpret_cast<uint16_t*>(s_ev + a.stage_cap);
-  uint16_t* s_rank = s_evp + a.stage_cap;
-  __shared__ u32 s_count;
+  uint16_t* s_evp = reinterpret_cast<uint16_t*>(s_ev + 4 * S1_EVW);
+  uint16_t* s_rank = s_evp + 4 * S1_EVW;
+  __shared__ u32 s_wcount[4];
   __shared__ u32 s_maxlen;
 
-  const u32 tid = threadIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const u32 ltmask = (1u << lane) - 1u;
   const int k = a.k, m = a.m, wlen = a.wlen;
   const u32 mmask = (1u << (2 * m)) - 1u;
   const u32 ban_mask = 0x55555555u & ((1u << (2 * (m - 2))) - 1u);
   const int rsh = 2 * (m - 1);
+  const u32 max_nk = (u32)a.max_nk;
 
   for (u32 p = tid; p < a.P; p += S1_THREADS) { s_hist[p] = 0; s_kc[p] = 0; }
   for (int j = 0; j < wlen; j++) s_ring[j * S1_THREADS + tid] = 0xFFFFFFFFu;
-  if (tid == 0) { s_count = 0; s_maxlen = 0; }
+  if (tid < 4) s_wcount[tid] = 0;
+  if (tid == 0) s_maxlen = 0;
   __syncthreads();
 
   u64 seg = (u64)blockIdx.x * S1_THREADS + tid;
@@ -253,17 +269,21 @@ s1_superk(const S1Args a)
   {
     u32 ml = len;
     for (int o = 16; o > 0; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
-    if ((tid & 31) == 0) atomicMax(&s_maxlen, ml);
+    if (lane == 0) atomicMax(&s_maxlen, ml);
   }
   __syncthreads();
   const u32 maxlen = s_maxlen;
+  if (maxlen == 0) return;
 
   // character reader: aligned 32-bit words + funnel shift
   const uint8_t* addr = a.text + start;
   const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
   const u32 csh = 8u * (u32)(reinterpret_cast<uintptr_t>(addr) & 3);
   const u32* wend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(a.text) + a.text_bytes + 3) & ~(uintptr_t)3);
-  u32 wprev = (len && wp < wend) ? __ldg(wp) : 0u;
+  // software pipeline: the word consumed in iteration t was requested in iteration t-2
+  auto ldw = [&](const u32* q) -> u32 { return (len && q < wend) ? __ldg(q) : 0u; };
+  u32 w0 = ldw(wp), w1 = ldw(wp + 1), w2 = ldw(wp + 2);
+  wp += 3;
 
   u32 fm = 0, rm = 0;                 // rolling forward / revcomp m-mer
   u32 pk = 0;                         // packed bases of the current 16-base word
@@ -272,37 +292,26 @@ s1_superk(const S1Args a)
   u32 cur_min = 0, cur_p = 0;
   u32 pre = 0xFFFFFFFFu;
   int j = 0;                          // m-mer index mod wlen (uniform)
+  u32* ring_col = s_ring + tid;
+  u32* evq = s_ev + wid * S1_EVW;
+  uint16_t* evpq = s_evp + wid * S1_EVW;
 
-  auto log_cut = [&](u32 end_excl) {
-    // the open record covers bases [end_excl - (k+nk-1), end_excl)
-    u32 slot = atomicAdd(&s_count, 1u);
-    s_ev[slot] = tid | ((end_excl - (u32)k - nk + 1u) << 7) | (nk << 18);
-    s_evp[slot] = (uint16_t)cur_p;
-    nk = 0;
-  };
-
-  for (u32 i0 = 0; i0 < maxlen; i0 += S1_ROUND) {
-    // fetch the 8 characters of this round (2 words)
-    u32 c4[2] = {0u, 0u};
-    if (i0 < len) {
+  // one extra step (i == len) acts as an invalid terminator that closes the last record
+  for (u32 i0 = 0; i0 <= maxlen; i0 += 4) {
+    const u32 c4 = __funnelshift_r(w0, w1, csh);
+    w0 = w1; w1 = w2;
+    w2 = (i0 + 8 < len + 4) ? ldw(wp) : 0u;
+    ++wp;
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        ++wp;
-        u32 wn = (wp < wend) ? __ldg(wp) : 0u;
-        c4[q] = __funnelshift_r(wprev, wn, csh);
-        wprev = wn;
-      }
-    }
-#pragma unroll
-    for (u32 ii = 0; ii < S1_ROUND; ii++) {
+    for (u32 ii = 0; ii < 4; ii++) {
       const u32 i = i0 + ii;
       const bool active = i < len;
-      const u32 ch = (c4[ii >> 2] >> (8 * (ii & 3))) & 0xFFu;
+      const u32 ch = (c4 >> (8 * ii)) & 0xFFu;
       const u32 c = (ch >> 1) & 3u;
       const bool valid = active && (((0x47544341u >> (8 * c)) & 0xFFu) == (ch & 0xDFu));   // "ACTG"[c]
       fm = ((fm << 2) | c) & mmask;
       rm = (rm >> 2) | ((c ^ 2u) << rsh);
-      pk = (pk << 2) | c;
+      if (active) pk = (pk << 2) | c;
       bad = valid ? max(bad - 1, 0) : k;
       u32 wmin = 0xFFFFFFFFu;
       if (i + 1 >= (u32)m) {                           // uniform
@@ -310,98 +319,95 @@ s1_superk(const S1Args a)
         u32 t = ~(canon | (canon >> 2));
         t = ((t >> 1) & t) & ban_mask;
         u32 lutv = t ? mmask : canon;
-        u32 s = (j + 1 < wlen) ? s_ring[(j + 1) * S1_THREADS + tid] : 0xFFFFFFFFu;
-        s_ring[j * S1_THREADS + tid] = lutv;
+        u32 s = (j + 1 < wlen) ? ring_col[(j + 1) * S1_THREADS] : 0xFFFFFFFFu;
+        ring_col[j * S1_THREADS] = lutv;
         pre = (j == 0) ? lutv : min(pre, lutv);
         wmin = min(s, pre);
-        if (++j == wlen) {
-          j = 0;
-          u32 accm = 0xFFFFFFFFu;
-          for (int t2 = wlen - 1; t2 >= 0; t2--) {
-            accm = min(accm, s_ring[t2 * S1_THREADS + tid]);
-            s_ring[t2 * S1_THREADS + tid] = accm;
-          }
-        }
+        if (++j == wlen) { j = 0; ring_suffix_min(ring_col, wlen); }
       }
-      if (active) {
-        const bool kvalid = (i + 1 >= (u32)k) && (bad == 0);
-        if (nk && (!kvalid || wmin != cur_min || nk == (u32)a.max_nk)) log_cut(i);
-        if (kvalid) {
-          if (nk == 0) { cur_min = wmin; cur_p = __ldg(a.repart + wmin); }
-          nk++;
+      // ---- cut decision (uniform code: ballot-allocated slot in the warp's event queue)
+      const bool kvalid = (i + 1 >= (u32)k) && (bad == 0);
+      const bool cut = (i <= len) && nk && (!kvalid || wmin != cur_min || nk == max_nk);
+      const u32 cmask = __ballot_sync(0xffffffffu, cut);
+      if (cmask) {
+        const u32 base = s_wcount[wid];
+        if (cut) {
+          const u32 slot = base + __popc(cmask & ltmask);
+          evq[slot] = tid | ((i - (u32)k - nk + 1u) << 7) | (nk << 18);    // record = bases [i-(k+nk-1), i)
+          evpq[slot] = (uint16_t)cur_p;
+          nk = 0;
         }
-        if (i + 1 == len) {
-          if (nk) log_cut(i + 1);
-          if ((i & 7u) != 7u) s_pack[(i >> 4) * S1_THREADS + tid] = pk << (2u * (15u - (i & 15u)));   // partial last word
-        }
+        __syncwarp();
+        if (lane == 0) s_wcount[wid] = base + __popc(cmask);
+        __syncwarp();
       }
+      if (kvalid) {
+        if (nk == 0) { cur_min = wmin; cur_p = __ldg(a.repart + wmin); }
+        nk++;
+      }
+      if (active && (i & 15u) == 15u) s_pack[(i >> 4) * S1_THREADS + tid] = pk;
     }
-    // bases [i0, i0+8) are complete for every active thread: publish the (half) word
-    if (i0 + 7 < len) s_pack[(i0 >> 4) * S1_THREADS + tid] = (i0 & 8u) ? pk : (pk << 16);
-    __syncthreads();
-    if (s_count > a.flush_thr || i0 + S1_ROUND >= maxlen) {
-      const u32 n = s_count;
-      for (u32 r = tid; r < n; r += S1_THREADS) {
-        u32 p = s_evp[r];
-        s_rank[r] = (uint16_t)atomicAdd(&s_hist[p], 1u);
-        atomicAdd(&s_kc[p], (s_ev[r] >> 18) & 127u);
-      }
-      __syncthreads();
-      for (u32 p = tid; p < a.P; p += S1_THREADS) {
-        u32 cnt = s_hist[p];
-        if (cnt) {
-          s_gbase[p] = atomicAdd(&a.cursor[p], cnt);
-          atomicAdd(&a.kcnt[p], (u64)s_kc[p]);
-          s_hist[p] = 0; s_kc[p] = 0;
-        }
-      }
-      __syncthreads();
-      uint4* out = reinterpret_cast<uint4*>(a.records);
-      for (u32 r = tid; r < n; r += S1_THREADS) {
-        const u32 ev = s_ev[r], p = s_evp[r];
-        const u32 t = ev & 127u, st = (ev >> 7) & 2047u, nkr = (ev >> 18) & 127u;
-        const u32 nb = (u32)k + nkr - 1u;                     // bases in the record
-        const u32 pos = s_gbase[p] + s_rank[r];
-        // V = bases [st, st+nb) as a big number: X >> s with X ending at word `top`
-        const int top = (int)((st + nb - 1u) >> 4);
-        const int s = 2 * (int)(15u - ((st + nb - 1u) & 15u));
-        if (W == 1) {
-          u32 v[4];
-#pragma unroll
-          for (int jw = 0; jw < 4; jw++) v[jw] = pack_word(s_pack, t, a.pack_words, top, s, jw);
-          // mask to 2*nb bits (nb <= 60), put nb in the top byte
-          const u32 bits = 2u * nb;
-#pragma unroll
-          for (int jw = 0; jw < 4; jw++) {
-            const int lo = 32 * jw;
-            if ((int)bits <= lo) v[jw] = 0u;
-            else if ((int)bits < lo + 32) v[jw] &= (1u << (bits - lo)) - 1u;
+    // every 8 bases: publish the partial word, decide (CTA-uniformly) whether to flush the events
+    if ((i0 & 4u) || i0 + 4 > maxlen) {
+      const u32 iend = min(i0 + 4u, len);              // bases [0, iend) of this thread are packed
+      if (iend && (iend & 15u)) s_pack[((iend - 1u) >> 4) * S1_THREADS + tid] = pk << (2u * (16u - (iend & 15u)));
+      const bool last = i0 + 4 > maxlen;
+      const int need = __syncthreads_or((int)(s_wcount[wid] > S1_EVTHR) | (int)last);
+      if (need) {
+        // pass 1: per-partition rank of every event, k-mer totals
+        for (u32 w = 0; w < 4; w++) {
+          const u32 n = s_wcount[w];
+          for (u32 r = tid; r < n; r += S1_THREADS) {
+            const u32 q = w * S1_EVW + r;
+            const u32 p = s_evp[q];
+            s_rank[q] = (uint16_t)atomicAdd(&s_hist[p], 1u);
+            atomicAdd(&s_kc[p], (s_ev[q] >> 18) & 127u);
           }
-          v[3] |= nb << 24;
-          if (pos < a.bcap[p]) out[a.boff[p] + pos] = make_uint4(v[0], v[1], v[2], v[3]);
-          else *a.overflow = 1u;
-        } else {
-          u32 v[8];
-#pragma unroll
-          for (int jw = 0; jw < 8; jw++) v[jw] = pack_word(s_pack, t, a.pack_words, top, s, jw);
-          const u32 bits = 2u * nb;
-#pragma unroll
-          for (int jw = 0; jw < 8; jw++) {
-            const int lo = 32 * jw;
-            if ((int)bits <= lo) v[jw] = 0u;
-            else if ((int)bits < lo + 32) v[jw] &= (1u << (bits - lo)) - 1u;
-          }
-          v[7] |= nb << 24;
-          if (pos < a.bcap[p]) {
-            uint4* dst = out + 2 * (a.boff[p] + pos);
-            dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
-          } else *a.overflow = 1u;
         }
+        __syncthreads();
+        for (u32 p = tid; p < a.P; p += S1_THREADS) {
+          u32 cnt = s_hist[p];
+          if (cnt) {
+            s_gbase[p] = atomicAdd(&a.cursor[p], cnt);
+            atomicAdd(&a.kcnt[p], (u64)s_kc[p]);
+            s_hist[p] = 0; s_kc[p] = 0;
+          }
+        }
+        __syncthreads();
+        // pass 2: build every record from the packed bases and store it
+        uint4* out = reinterpret_cast<uint4*>(a.records);
+        for (u32 w = 0; w < 4; w++) {
+          const u32 n = s_wcount[w];
+          for (u32 r = tid; r < n; r += S1_THREADS) {
+            const u32 q = w * S1_EVW + r;
+            const u32 ev = s_ev[q], p = s_evp[q];
+            const u32 t = ev & 127u, st = (ev >> 7) & 2047u, nkr = (ev >> 18) & 127u;
+            const u32 nb = (u32)k + nkr - 1u;                     // bases in the record
+            const u32 pos = s_gbase[p] + s_rank[q];
+            const int top = (int)((st + nb - 1u) >> 4);
+            const int s = 2 * (int)(15u - ((st + nb - 1u) & 15u));
+            const u32 bits = 2u * nb;
+            u32 v[4 * W];
+#pragma unroll
+            for (int jw = 0; jw < 4 * W; jw++) {
+              u32 x = pack_word(s_pack, t, a.pack_words, top, s, jw);
+              const int lo = 32 * jw;
+              if ((int)bits <= lo) x = 0u;
+              else if ((int)bits < lo + 32) x &= (1u << (bits - lo)) - 1u;
+              v[jw] = x;
+            }
+            v[4 * W - 1] |= nb << 24;
+            if (pos < a.bcap[p]) {
+              uint4* dst = out + (size_t)W * (a.boff[p] + pos);
+              dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+              if (W == 2) dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+            } else *a.overflow = 1u;
+          }
+        }
+        __syncthreads();
+        if (tid < 4) s_wcount[tid] = 0;
+        __syncthreads();
       }
-      __syncthreads();
-      if (tid == 0) s_count = 0;
-      __syncthreads();
     }
   }
 }
@@ -411,7 +417,8 @@ s1_superk(const S1Args a)
 // ------------------------------------------------------------------------------------
 size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P)
 {
-  return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)stage_cap * 8;
+  (void)stage_cap;
+  return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)4 * S1_EVW * 8;
 }
 
 cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,

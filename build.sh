@@ -18,3 +18,7 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT kmtricks_b200/_build/*.o -lcudart -ldl
 echo "built $OUT"
+# C++ host (CLI + run-dir + IMergePlugin host) over the C ABI
+mkdir -p kmtricks_b200/bin
+g++ -std=c++17 -O2 -Wall -Iinclude -o kmtricks_b200/bin/kmx kmtricks_b200/csrc/host/kmx_main.cpp -Lkmtricks_b200 -lkmx_sm100 -ldl -lz -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
+echo "built kmtricks_b200/bin/kmx"

@@ -287,14 +287,17 @@ s1_superk(const S1Args a)
 
   u32 fm = 0, rm = 0;                 // rolling forward / revcomp m-mer
   u32 pk = 0;                         // packed bases of the current 16-base word
-  int bad = 0;                        // >0 : k-mer ending here is invalid
+  int bad = k;                        // valid bases still missing before the k-mer ending here is valid
   u32 nk = 0;                         // k-mers in the open record
   u32 cur_min = 0, cur_p = 0;
   u32 pre = 0xFFFFFFFFu;
   int j = 0;                          // m-mer index mod wlen (uniform)
+  u32 wcnt = 0;                       // events in this warp's queue (same value in every lane)
   u32* ring_col = s_ring + tid;
   u32* evq = s_ev + wid * S1_EVW;
   uint16_t* evpq = s_evp + wid * S1_EVW;
+  const uint16_t* __restrict__ repart = a.repart;
+  const u32 mm1 = (u32)m - 1u;
 
   // one extra step (i == len) acts as an invalid terminator that closes the last record
   for (u32 i0 = 0; i0 <= maxlen; i0 += 4) {
@@ -313,47 +316,42 @@ s1_superk(const S1Args a)
       rm = (rm >> 2) | ((c ^ 2u) << rsh);
       if (active) pk = (pk << 2) | c;
       bad = valid ? max(bad - 1, 0) : k;
-      u32 wmin = 0xFFFFFFFFu;
-      if (i + 1 >= (u32)m) {                           // uniform
-        u32 canon = min(fm, rm);
-        u32 t = ~(canon | (canon >> 2));
-        t = ((t >> 1) & t) & ban_mask;
-        u32 lutv = t ? mmask : canon;
-        u32 s = (j + 1 < wlen) ? ring_col[(j + 1) * S1_THREADS] : 0xFFFFFFFFu;
-        ring_col[j * S1_THREADS] = lutv;
-        pre = (j == 0) ? lutv : min(pre, lutv);
-        wmin = min(s, pre);
-        if (++j == wlen) { j = 0; ring_suffix_min(ring_col, wlen); }
-      }
+      // lut value of the m-mer ending here (garbage before base m-1: it only feeds windows of
+      // k-mers that are not valid yet)
+      u32 canon = min(fm, rm);
+      u32 t = ~(canon | (canon >> 2));
+      t = ((t >> 1) & t) & ban_mask;
+      const u32 lutv = (t || i < mm1) ? mmask : canon;
+      const u32 s = (j + 1 < wlen) ? ring_col[(j + 1) * S1_THREADS] : 0xFFFFFFFFu;
+      ring_col[j * S1_THREADS] = lutv;
+      pre = (j == 0) ? lutv : min(pre, lutv);
+      const u32 wmin = min(s, pre);
+      if (++j == wlen) { j = 0; ring_suffix_min(ring_col, wlen); }
       // ---- cut decision (uniform code: ballot-allocated slot in the warp's event queue)
-      const bool kvalid = (i + 1 >= (u32)k) && (bad == 0);
-      const bool cut = (i <= len) && nk && (!kvalid || wmin != cur_min || nk == max_nk);
+      const bool kvalid = bad == 0;
+      const bool cut = nk && (!kvalid || wmin != cur_min || nk == max_nk);
       const u32 cmask = __ballot_sync(0xffffffffu, cut);
-      if (cmask) {
-        const u32 base = s_wcount[wid];
-        if (cut) {
-          const u32 slot = base + __popc(cmask & ltmask);
-          evq[slot] = tid | ((i - (u32)k - nk + 1u) << 7) | (nk << 18);    // record = bases [i-(k+nk-1), i)
-          evpq[slot] = (uint16_t)cur_p;
-          nk = 0;
-        }
-        __syncwarp();
-        if (lane == 0) s_wcount[wid] = base + __popc(cmask);
-        __syncwarp();
+      if (cut) {
+        const u32 slot = wcnt + __popc(cmask & ltmask);
+        evq[slot] = tid | ((i - (u32)k - nk + 1u) << 7) | (nk << 18);    // record = bases [i-(k+nk-1), i)
+        evpq[slot] = (uint16_t)cur_p;
+        nk = 0;
       }
-      if (kvalid) {
-        if (nk == 0) { cur_min = wmin; cur_p = __ldg(a.repart + wmin); }
-        nk++;
-      }
-      if (active && (i & 15u) == 15u) s_pack[(i >> 4) * S1_THREADS + tid] = pk;
+      wcnt += __popc(cmask);
+      if (kvalid && nk == 0) { cur_min = wmin; cur_p = __ldg(repart + wmin); }
+      nk += kvalid ? 1u : 0u;
     }
+    if ((i0 & 12u) == 12u && i0 + 3 < len) s_pack[(i0 >> 4) * S1_THREADS + tid] = pk;
     // every 8 bases: publish the partial word, decide (CTA-uniformly) whether to flush the events
     if ((i0 & 4u) || i0 + 4 > maxlen) {
       const u32 iend = min(i0 + 4u, len);              // bases [0, iend) of this thread are packed
       if (iend && (iend & 15u)) s_pack[((iend - 1u) >> 4) * S1_THREADS + tid] = pk << (2u * (16u - (iend & 15u)));
       const bool last = i0 + 4 > maxlen;
-      const int need = __syncthreads_or((int)(s_wcount[wid] > S1_EVTHR) | (int)last);
+      const int need = __syncthreads_or((int)(wcnt > S1_EVTHR) | (int)last);
       if (need) {
+        if (lane == 0) s_wcount[wid] = wcnt;
+        wcnt = 0;
+        __syncthreads();
         // pass 1: per-partition rank of every event, k-mer totals
         for (u32 w = 0; w < 4; w++) {
           const u32 n = s_wcount[w];

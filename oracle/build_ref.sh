@@ -142,4 +142,10 @@ for h in "$HERE"/ref_harness/*.cpp; do
   b=$(basename "$h" .cpp)
   g++ -o "$OUT/bin/$b" "$OBJ/h_$b.o" "$OUT/libkmref.a" -lz -lpthread -ldl
 done
+# the reference's example plugins, UNCHANGED (plugins/example/*.cpp): acceptance test of the plugin host ABI
+mkdir -p "$OUT/plugins"
+for pl in "$REF"/plugins/example/*.cpp; do
+  b=$(basename "$pl" .cpp)
+  g++ $CXXF $INC -shared "$pl" -o "$OUT/plugins/lib$b.so"
+done
 echo "oracle/_ref built: $(ls "$OUT/bin" | tr '\n' ' ')"

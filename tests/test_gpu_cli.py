@@ -1,0 +1,115 @@
+"""The C++ host (kmtricks_b200/bin/kmx: CLI + run-dir + plugin host over the C ABI) against the
+unmodified reference CLI on the same fof: every file the two run directories share must be
+byte-identical.  Also loads the reference's own example plugins, compiled unchanged."""
+import filecmp
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KMX = os.path.join(ROOT, "kmtricks_b200", "bin", "kmx")
+REF = os.path.join(ROOT, "oracle", "_ref", "bin", "kmtricks")
+PLUG = os.path.join(ROOT, "oracle", "_ref", "plugins")
+
+
+@pytest.fixture(scope="module")
+def workdir():
+    from kmtricks_b200 import synth
+    from tests.conftest import EDGE_FASTA, EDGE_FASTQ_CRLF
+    if not (os.path.exists(KMX) and os.path.exists(REF)):
+        pytest.skip("kmx or the reference binary is not built")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="kmx_cli_", dir=base)
+    with open(f"{d}/fof.txt", "w") as f:
+        for s in range(4):
+            open(f"{d}/S{s}.fastq", "wb").write(synth.make_fastq(5, s, 20_000, L=150, G=100_000, d=4e-3, e=4e-3, revcomp=True))
+            f.write(f"S{s}: {d}/S{s}.fastq" + (" ! 1" if s == 2 else "") + "\n")
+        open(f"{d}/edge.fasta", "wb").write(EDGE_FASTA); open(f"{d}/crlf.fastq", "wb").write(EDGE_FASTQ_CRLF)
+        f.write(f"E1 : {d}/edge.fasta ; {d}/crlf.fastq\n")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
+def run_both(d, tag, args):
+    common = ["pipeline", "--file", f"{d}/fof.txt", "--nb-partitions", "8", "--minimizer-size", "10", "--static-repart", "--keep-tmp"] + args
+    a, b = f"{d}/ref_{tag}", f"{d}/kmx_{tag}"
+    subprocess.run([REF] + common + ["--run-dir", a, "-t", "4"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([KMX] + common + ["--run-dir", b, "--threads", "3"], check=True)
+    return a, b
+
+
+def same_files(a, b, sub, must_exist=True):
+    names = sorted(os.listdir(os.path.join(a, sub)))
+    if must_exist:
+        assert names, f"reference wrote nothing under {sub}"
+    for n in names:
+        pa, pb = os.path.join(a, sub, n), os.path.join(b, sub, n)
+        if os.path.isdir(pa):
+            same_files(a, b, os.path.join(sub, n), must_exist)
+        else:
+            assert os.path.exists(pb), f"missing {sub}/{n}"
+            assert filecmp.cmp(pa, pb, shallow=False), f"{sub}/{n} differs"
+
+
+@pytest.mark.parametrize("tag,args", [
+    ("kmer_count", ["--kmer-size", "31", "--mode", "kmer:count:bin", "--hard-min", "2"]),
+    ("kmer_pa_k63", ["--kmer-size", "63", "--mode", "kmer:pa:bin", "--hard-min", "1", "--soft-min", "3", "--share-min", "2", "--recurrence-min", "2"]),
+    ("hash_bf", ["--kmer-size", "31", "--mode", "hash:bf:bin", "--hard-min", "2", "--bloom-size", "2000000", "--soft-min", "2", "--share-min", "1"]),
+    ("hash_count", ["--kmer-size", "31", "--mode", "hash:count:bin", "--hard-min", "2", "--bloom-size", "2000000"]),
+])
+def test_run_dir_equals_reference(workdir, tag, args):
+    a, b = run_both(workdir, tag, args)
+    for sub in ("matrices", "merge_infos", "partition_infos", "counts", "repartition_gatb"):
+        same_files(a, b, sub)
+    assert filecmp.cmp(f"{a}/hash.info", f"{b}/hash.info", shallow=False)
+    if tag == "hash_bf":
+        same_files(a, b, "fpr")
+
+
+def test_template_example_plugin_fails_like_the_reference(workdir):
+    """plugins/example/template_ex.cpp exports no `destroy`, so the reference refuses it
+    (plugin_manager.hpp:73-79, PluginError); the kmx plugin host must fail the same loud way."""
+    so = os.path.join(PLUG, "libtemplate_ex.so")
+    if not os.path.exists(so):
+        pytest.skip("reference plugins not built")
+    common = ["pipeline", "--file", f"{workdir}/fof.txt", "--nb-partitions", "8", "--static-repart", "--kmer-size", "31",
+              "--mode", "kmer:count:bin", "--plugin", so, "--plugin-config", "3"]
+    r1 = subprocess.run([REF] + common + ["--run-dir", f"{workdir}/ref_tpl"], capture_output=True, text=True)
+    r2 = subprocess.run([KMX] + common + ["--run-dir", f"{workdir}/kmx_tpl"], capture_output=True, text=True)
+    assert r1.returncode != 0 and r2.returncode != 0
+    assert "destroy" in r2.stderr
+
+
+@pytest.mark.parametrize("lib,cfg,k", [("libbasic_ex.so", "2", "31"), ("libbasic_ex.so", "3", "45")])
+def test_reference_example_plugins_load_unchanged(workdir, lib, cfg, k):
+    """plugins/example/{basic,template}_ex.cpp compiled as they are (oracle/build_ref.sh) must load in
+    the kmx plugin host and produce the matrices the reference produces with the same plugin."""
+    so = os.path.join(PLUG, lib)
+    if not os.path.exists(so):
+        pytest.skip("reference plugins not built")
+    a, b = run_both(workdir, f"plug_{lib[3:8]}_{k}", ["--kmer-size", k, "--mode", "kmer:count:bin", "--hard-min", "1",
+                                                     "--plugin", so, "--plugin-config", cfg])
+    same_files(a, b, "matrices")
+    same_files(a, b, "merge_infos")
+
+
+def test_repart_from_and_until_count(workdir):
+    d = workdir
+    a, b = run_both(d, "base", ["--kmer-size", "31", "--mode", "kmer:count:bin", "--hard-min", "2"])
+    # reuse the reference's repartition file (--repart-from) and stop after counting
+    subprocess.run([KMX, "pipeline", "--file", f"{d}/fof.txt", "--run-dir", f"{d}/kmx_rf", "--nb-partitions", "8", "--kmer-size", "31",
+                    "--mode", "kmer:count:bin", "--hard-min", "2", "--repart-from", a, "--until", "count"], check=True)
+    same_files(a, f"{d}/kmx_rf", "counts")
+    assert os.listdir(f"{d}/kmx_rf/matrices") == []
+
+
+def test_cli_errors_are_loud(workdir):
+    r = subprocess.run([KMX, "pipeline", "--file", f"{workdir}/nope.txt", "--run-dir", f"{workdir}/x", "--nb-partitions", "4"], capture_output=True, text=True)
+    assert r.returncode != 0 and "error" in r.stderr.lower()
+    r = subprocess.run([KMX, "pipeline", "--file", f"{workdir}/fof.txt", "--run-dir", f"{workdir}/x"], capture_output=True, text=True)
+    assert r.returncode != 0

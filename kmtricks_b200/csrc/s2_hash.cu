@@ -23,11 +23,14 @@ static constexpr int HH_WARPS = HH_THREADS / 32;
 // grid: (x tiles, P).  Each warp takes 32 records at a time, stages them in shared memory with
 // the prefix sum of their k-mer counts, and then walks the k-mers of those records with all 32
 // lanes busy (lane t -> k-mer t, t+32, ...; the owning record is found by a 5-step binary
-// search in the warp's prefix array).  The histogram update is a fire-and-forget RED.
-template <int W>
+// search in the warp's prefix array).  Every lane runs the same instruction stream (a rolling
+// variant with per-lane contiguous chunks was measured 1.9x SLOWER: lanes cross record
+// boundaries at different steps, so the warp pays extract + roll at every step).
+// The histogram update is a fire-and-forget RED; the modulo is an exact 32-bit Barrett when W < 2^32.
+template <int W, bool D32>
 __global__ void __launch_bounds__(HH_THREADS)
 hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
-                 int k, u64 Wbits, FastMod64 fm, u32* __restrict__ hist)
+                 int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist)
 {
   __shared__ uint4 s_rec[HH_WARPS][32 * W];
   __shared__ u32 s_pref[HH_WARPS][33];
@@ -70,7 +73,7 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
         u64 hh = (u64)v.z | ((u64)v.w << 32);
         rec.n = (int)(hh >> 56); rec.hi = hh & 0x00FFFFFFFFFFFFFFULL;
         u64 c; canon1(rec, k, j, c);
-        key = fastmod64(xxh64_8(c), fm);
+        { const u64 hv = xxh64_8(c); key = D32 ? (u64)fastmod64_d32(hv, fm32) : fastmod64(hv, fm); }
       } else {
         uint4 a = s_rec[w][2 * q], b = s_rec[w][2 * q + 1];
         Rec2 rec;
@@ -79,7 +82,7 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
         u64 hh = (u64)b.z | ((u64)b.w << 32);
         rec.n = (int)(hh >> 56); rec.v3 = hh & 0x00FFFFFFFFFFFFFFULL;
         u64 clo, chi; canon2(rec, k, j, clo, chi);
-        key = fastmod64(xxh64_16(clo, chi), fm);
+        { const u64 hv = xxh64_16(clo, chi); key = D32 ? (u64)fastmod64_d32(hv, fm32) : fastmod64(hv, fm); }
       }
       atomicAdd(h + key, 1u);       // result unused -> RED.ADD
     }
@@ -171,10 +174,13 @@ cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_ml
   if (gx > 592) gx = 592;                 // 4 waves of 148 SMs per partition row at most
   dim3 grid(gx, c.P);
   u32 hmin = hard_min ? hard_min : 1;
-  if (c.W == 1)
-    hash_hist_kernel<1><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist);
-  else
-    hash_hist_kernel<2><<<grid, HH_THREADS, 0, st>>>((const uint4*)c.records, c.boff, c.bcnt, c.k, Wbits, fm, hist);
+  FastMod32 f32; f32.d = (u32)mod_d; f32.m64 = mod_d >= 2 ? (~0ULL) / mod_d : 0;   // floor((2^64-1)/d) == floor(2^64/d) unless d | 2^64 (d=2^j): still a valid Barrett constant
+  const bool d32 = mod_d >= 2 && mod_d < (1ULL << 32);
+  const uint4* recs = (const uint4*)c.records;
+  if (c.W == 1 && d32) hash_hist_kernel<1, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist);
+  else if (c.W == 1) hash_hist_kernel<1, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist);
+  else if (d32) hash_hist_kernel<2, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist);
+  else hash_hist_kernel<2, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist);
   hash_count_kernel<<<c.P * S, HC_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_counts);
   *launches += 2;
   return cudaGetLastError();

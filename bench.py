@@ -298,13 +298,17 @@ def main_kmx(args):
     sizes = (C.c_size_t * N)(*([sample_bytes] * N))
     hmins = (C.c_uint32 * N)(*([args.hard_min] * N))
 
+    body_max = [0]; body_sum = [0]
+
     def merges(to_host=None):
+        body_sum[0] = 0
         for j, p in enumerate(my_parts):
             if to_host is None and fmt in ("bf", "bft"):
                 tm("set_out", L.kmx_set_merge_output, h, d_out.value + j * (slab_bytes + 64), slab_bytes + 64)
             tm("merge", L.kmx_merge_partition, h, p, C.byref(mp), C.byref(res))
+            body_max[0] = max(body_max[0], res.n_rows * res.row_bytes); body_sum[0] += res.n_rows * res.row_bytes
             if to_host is not None:
-                tm("merge_get", L.kmx_merge_get, h, to_host + j * slab_bytes, None, None)
+                tm("merge_get", L.kmx_merge_get, h, to_host + (j * slab_bytes if fmt in ("bf", "bft") else 0), None, None)
         tm("set_out", L.kmx_set_merge_output, h, None, 0)
 
     def make_step(ptrs, on_device, lanes, to_host=None):
@@ -393,8 +397,8 @@ def main_kmx(args):
             alg = BUCKET_BYTES_PER_KMER * kmers_launch
             what = "S2: buckets read (1.03 B/k-mer) [+12 B per surviving (key,sample)]"
         else:
-            alg = slab_bytes
-            what = "S3/S4: slab written"
+            alg = body_sum[0] / max(len(my_parts), 1)
+            what = "S3/S4: matrix body written"
         ach = alg / (dur_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "algorithmic_bytes_per_launch": alg, "launch_ms": dur_ms, "what": what, "peak_source": peak_src}
@@ -416,7 +420,8 @@ def main_kmx(args):
         if world > 1:
             t = torch.tensor([K], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN); K = int(t.item())
         rc = L.kmx_host_alloc(K * sample_bytes, C.byref(h_text))
-        rc2 = L.kmx_host_alloc(max(len(my_parts) * slab_bytes, 64), C.byref(h_out))
+        out_bytes = len(my_parts) * slab_bytes if fmt in ("bf", "bft") else int(body_max[0] * 1.05) + 4096
+        rc2 = L.kmx_host_alloc(max(out_bytes, 64), C.byref(h_out))
         if rc or rc2:
             e2e = {"value": None, "unit": "k-mers/s", "error": "pinned host allocation failed"}
         else:
@@ -429,7 +434,7 @@ def main_kmx(args):
             ms_e = timed(step_host, ns)
             wall_e = time.perf_counter() - t0
             e2e = {"value": world * kmers_step / (ms_e / ns * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": N * sample_bytes * world,
-                   "d2h_bytes_per_step": len(my_parts) * slab_bytes * world, "ms_per_step": ms_e / ns, "wall_s_per_step": wall_e / ns,
+                   "d2h_bytes_per_step": int(body_sum[0]) * world, "ms_per_step": ms_e / ns, "wall_s_per_step": wall_e / ns,
                    "what": "kmx_run_samples on pinned host FASTQ + kmx_merge_partition/kmx_merge_get into pinned host memory",
                    "host_text_samples": K}
             L.kmx_host_free(h_text); L.kmx_host_free(h_out)

@@ -543,7 +543,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min)
   void* kp = nullptr; void* cp = nullptr;
   CK(arena_alloc(ctx, D * 8, &kp));
   CK(arena_alloc(ctx, D * 4, &cp));
-  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->st, &ln->launches)); }
+  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->d_cursor, ln->st, &ln->launches)); }
   for (u32 p = 0; p < P; p++) {
     ListRef& L = ctx->lists[(size_t)sample * P + p];
     u64 b = h_so[(size_t)p * S], e = h_so[(size_t)(p + 1) * S];

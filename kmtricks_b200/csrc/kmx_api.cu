@@ -516,7 +516,9 @@ extern "C" int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition) { if 
 // ---------------------------------------------------------------------------------------
 static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min);
 
-static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min)
+// win_sample / win_part (host, [P], optional): window v of the histogram holds partition win_part[v] of
+// sample slot win_sample[v] (multi-GPU: one pass counts the same partitions of several samples)
+static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u32* win_sample = nullptr, const u32* win_part = nullptr)
 {
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
@@ -543,12 +545,24 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min)
   void* kp = nullptr; void* cp = nullptr;
   CK(arena_alloc(ctx, D * 8, &kp));
   CK(arena_alloc(ctx, D * 4, &cp));
-  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->d_cursor, ln->st, &ln->launches)); }
-  for (u32 p = 0; p < P; p++) {
-    ListRef& L = ctx->lists[(size_t)sample * P + p];
-    u64 b = h_so[(size_t)p * S], e = h_so[(size_t)(p + 1) * S];
+  const u32* d_wpart = nullptr;
+  if (win_part) {
+    CK(ensure(ln, ln->tmp_cnt, (size_t)P * 4 + 64));
+    // h_so was consumed above (D) but is still needed below: stage the map behind it
+    u32* hp = (u32*)(ln->h_pin + ((size_t)P * S + 1) * 8);
+    memcpy(hp, win_part, (size_t)P * 4);
+    CK(cudaMemcpyAsync(ln->tmp_cnt.p, hp, (size_t)P * 4, cudaMemcpyHostToDevice, ln->st));
+    d_wpart = (const u32*)ln->tmp_cnt.p;
+  }
+  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->d_cursor, d_wpart, ln->st, &ln->launches)); }
+  for (u32 v = 0; v < P; v++) {
+    u64 b = h_so[(size_t)v * S], e = h_so[(size_t)(v + 1) * S];
+    if (win_part && ln->h_cursor[v] == 0) continue;       // unused window
+    const u32 smp = win_sample ? win_sample[v] : sample, prt = win_part ? win_part[v] : v;
+    ListRef& L = ctx->lists[(size_t)smp * P + prt];
     L.lo = (u64*)kp + b; L.hi = nullptr; L.cnt = (u32*)cp + b; L.n = e - b;
   }
+  if (win_part) CK(cudaStreamSynchronize(ln->st));        // pinned map staging is reused
   return KMX_OK;
 }
 

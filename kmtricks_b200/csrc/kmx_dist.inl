@@ -138,6 +138,35 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
   // ---- stage 2 for every rank's sample of this batch, restricted to my partitions
   DBuf save_rec = ln->records;
   std::vector<u64> save_boff = ln->h_boff, save_kcnt = ln->h_kcnt; std::vector<u32> save_bcap = ln->h_bcap, save_cur = ln->h_cursor;
+  const u32 Pown = myl - myf;
+  const bool hist_path = ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok == 1;
+  if (hist_path && (u64)G * Pown <= P && Pown > 0) {
+    // ONE pass: histogram window v = g*Pown + (p - myf) holds partition p of rank g's sample; all
+    // hard-mins of a batch are equal in practice, otherwise fall through to the per-source passes
+    bool same_hm = true;
+    for (int g = 1; g < G; g++) if (meta[(size_t)g * ML + 3 * P + 1] != meta[3 * P + 1]) same_hm = false;
+    if (same_hm) {
+      std::vector<u32> wsmp(P, 0), wprt(P, 0);
+      for (u32 v = 0; v < P; v++) { ln->h_boff[v] = 0; ln->h_cursor[v] = 0; ln->h_bcap[v] = 0; ln->h_kcnt[v] = 0; }
+      for (int g = 0; g < G; g++) {
+        const u64* mg = &meta[(size_t)g * ML];
+        for (u32 p = myf; p < myl; p++) {
+          const u32 v = (u32)g * Pown + (p - myf);
+          ln->h_boff[v] = roff[g] + (mg[p] - mg[myf]);
+          ln->h_cursor[v] = (u32)mg[P + 1 + p]; ln->h_bcap[v] = ln->h_cursor[v];
+          ln->h_kcnt[v] = mg[2 * P + 1 + p];
+          wsmp[v] = (u32)g * n_local + i_local; wprt[v] = p;
+        }
+      }
+      ln->records.p = rbuf;
+      rc = upload_bucket_meta(ln);
+      ln->sample_ready = true;
+      for (int g = 0; g < G; g++) for (u32 p = 0; p < P; p++) ctx->lists[((size_t)g * n_local + i_local) * P + p] = ListRef();
+      if (!rc) rc = count_hash_hist(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data());
+      ln->records = save_rec; ln->h_boff = save_boff; ln->h_kcnt = save_kcnt; ln->h_bcap = save_bcap; ln->h_cursor = save_cur;
+      return rc;
+    }
+  }
   for (int g = 0; g < G && !rc; g++) {
     const u64* mg = &meta[(size_t)g * ML];
     for (u32 p = 0; p < P; p++) {

@@ -55,7 +55,7 @@ cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_ml
                              u32* hist /* P*Wbits */, u32 hard_min, u32* sub_counts /* P*S */, u32 S,
                              cudaStream_t st, u64* launches);
 cudaError_t launch_hash_emit(u32 P, u64 Wbits, u32 S, u32* hist, u32 hard_min, const u64* sub_off,
-                             u64* out_keys, u32* out_counts, const u32* bcnt, cudaStream_t st, u64* launches);
+                             u64* out_keys, u32* out_counts, const u32* bcnt, const u32* win_part, cudaStream_t st, u64* launches);
 cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
 
 // generic path: expand -> keys, segmented radix sort, run-length

@@ -117,7 +117,8 @@ hash_count_kernel(u64 Wbits, u32 S, const u32* __restrict__ hist, u32 hmin, u32*
 static constexpr int HE_THREADS = 256;
 __global__ void __launch_bounds__(HE_THREADS)
 hash_emit_kernel(u64 Wbits, u32 S, u32* __restrict__ hist, u32 hmin, const u64* __restrict__ sub_off,
-                 u64* __restrict__ out_keys, u32* __restrict__ out_counts, const u32* __restrict__ bcnt)
+                 u64* __restrict__ out_keys, u32* __restrict__ out_counts, const u32* __restrict__ bcnt,
+                 const u32* __restrict__ win_part /* NULL: window p holds partition p */)
 {
   __shared__ u32 s_warp[HE_THREADS / 32];
   __shared__ u32 s_run;
@@ -126,7 +127,7 @@ hash_emit_kernel(u64 Wbits, u32 S, u32* __restrict__ hist, u32 hmin, const u64* 
   const u64 slot0 = (u64)s * HIST_SUB;
   const u64 slot1 = min(Wbits, slot0 + HIST_SUB);
   uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)p * Wbits);   // W multiple of 64 -> aligned
-  const u64 key_base = (u64)p * Wbits;
+  const u64 key_base = (u64)(win_part ? win_part[p] : p) * Wbits;
   u64 obase = sub_off[blockIdx.x];
   if (sub_off[blockIdx.x + 1] == obase) {
     // nothing survives here: still has to clear non-zero (below hard-min) slots
@@ -190,10 +191,10 @@ cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_ml
 }
 
 cudaError_t launch_hash_emit(u32 P, u64 Wbits, u32 S, u32* hist, u32 hard_min, const u64* sub_off,
-                             u64* out_keys, u32* out_counts, const u32* bcnt, cudaStream_t st, u64* launches)
+                             u64* out_keys, u32* out_counts, const u32* bcnt, const u32* win_part, cudaStream_t st, u64* launches)
 {
   u32 hmin = hard_min ? hard_min : 1;
-  hash_emit_kernel<<<P * S, HE_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_off, out_keys, out_counts, bcnt);
+  hash_emit_kernel<<<P * S, HE_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_off, out_keys, out_counts, bcnt, win_part);
   *launches += 1;
   return cudaGetLastError();
 }

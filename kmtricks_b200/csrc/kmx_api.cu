@@ -19,14 +19,22 @@ using namespace kmx;
 namespace kmx {
 size_t scan_u32_work_bytes(u64 n);
 cudaError_t scan_u32_inplace(u32* d, u64 n, u32* d_total, void* work, cudaStream_t st, u64* launches);
-size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off);
-cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, u64* lo, u64* hi, u64* lo_alt, u64* hi_alt,
+size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off, const u64* h_seg_end = nullptr);
+cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, const u64* h_seg_end, u64* lo, u64* hi, u64* lo_alt, u64* hi_alt,
                                  int W, int begin_bit, int end_bit, void* d_work, int* result_in_alt,
                                  cudaStream_t st, u64* launches);
 size_t rle_work_bytes(u32 nseg, const u64* h_seg_off);
 cudaError_t rle_segments(u32 nseg, const u64* h_seg_off, const u64* lo, const u64* hi, int W, u32 hard_min,
                          void* d_work, std::vector<u64>& h_tile_off, std::vector<u64>& h_seg_out_off,
                          int phase, u64* out_lo, u64* out_hi, u32* out_cnt, cudaStream_t st, u64* launches);
+cudaError_t launch_ht_insert_records(const S2Common& c, u64* keys, u32* cnts, const u64* toff, const u64* tcap, u32* overflow,
+                                     cudaStream_t st, u64* launches);
+cudaError_t launch_ht_compact(u32 P, u64 max_cap, const u64* keys, const u32* cnts, const u64* toff, const u64* tcap, u32 hard_min,
+                              u64* out, u32* pcnt, cudaStream_t st, u64* launches);
+cudaError_t launch_ht_lookup(u32 P, u32 max_n, const u64* keys, const u32* cnts, const u64* toff, const u64* tcap, const u64* skeys,
+                             const u64* soff, const u32* pcnt, const u64* oo, u64* out_keys, u32* out_cnt, cudaStream_t st, u64* launches);
+cudaError_t launch_ht_union(const MergeList* d_lists, u32 N, u64 max_n, u64* keys, u32* cnts, u64 cap, u32* overflow,
+                            u64* out, u32* count, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_solid(const MergeList* d_lists, u32 N, const u32* d_soft, const u64* ulo, const u64* uhi,
                                 u64 nu, int W, u32* solid_in, u64 max_n, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_emit(const MergeList* d_lists, u32 N, const u32* d_soft, u32 rmin, u32 share, u32 emit_all,
@@ -72,7 +80,7 @@ struct Lane {
   char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
   DBuf hist, sub_counts, sub_off;
-  DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt;
+  DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt, ht_keys, ht_cnts;
   // ---- profiling
   std::vector<ProfSpan> prof_spans;
   std::vector<cudaEvent_t> prof_pool;
@@ -88,6 +96,8 @@ struct kmx_ctx {
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
+  double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
+  bool ht_union_ok = true;
   bool prof_on = false;
   double prof_ms[KMX_PROF_KINDS] = {0};
   u64 prof_cnt[KMX_PROF_KINDS] = {0};
@@ -221,7 +231,7 @@ static void lane_destroy(Lane* ln)
   kmx_ctx* ctx = ln->ctx;
   if (ln->st) cudaStreamSynchronize(ln->st);
   DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->records, &ln->hist,
-                  &ln->sub_counts, &ln->sub_off, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt};
+                  &ln->sub_counts, &ln->sub_off, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
   for (void* p : singles) if (p) cudaFree(p);
@@ -515,6 +525,8 @@ extern "C" int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition) { if 
 // stage 2
 // ---------------------------------------------------------------------------------------
 static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min);
+static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min);
+static const int KMX_HT_FALLBACK = -1000;   // internal: table overflowed, use the sort path
 
 // win_sample / win_part (host, [P], optional): window v of the histogram holds partition win_part[v] of
 // sample slot win_sample[v] (multi-GPU: one pass counts the same partitions of several samples)
@@ -584,6 +596,10 @@ static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
       ok = ctx->hist_ok;
     }
     if (ok == 1) return count_hash_hist(ln, sample, hard_min);
+  }
+  if (ctx->prm.key_kind == KMX_KEY_KMER && ctx->W == 1) {
+    int rc = count_kmer_ht(ln, sample, hard_min);
+    if (rc != KMX_HT_FALLBACK) return rc;
   }
   return count_generic(ln, sample, hard_min);
 }

@@ -31,7 +31,7 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min)
   const int end_bit = hash ? bit_length(Wb * P - 1) : 2 * (int)ctx->prm.kmer_size;
   int in_alt = 0;
   { PROF(KMX_PROF_SORT);
-  CK(segmented_radix_sort(P, koff.data(), (u64*)ln->keys_lo.p, (u64*)ln->keys_hi.p, (u64*)ln->keys_lo2.p, (u64*)ln->keys_hi2.p,
+  CK(segmented_radix_sort(P, koff.data(), nullptr, (u64*)ln->keys_lo.p, (u64*)ln->keys_hi.p, (u64*)ln->keys_lo2.p, (u64*)ln->keys_hi2.p,
                           KW, 0, end_bit, ln->sort_work.p, &in_alt, ln->st, &ln->launches)); }
   const u64* slo = (const u64*)(in_alt ? ln->keys_lo2.p : ln->keys_lo.p);
   const u64* shi = (const u64*)(in_alt ? ln->keys_hi2.p : ln->keys_hi.p);
@@ -51,6 +51,79 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min)
   return KMX_OK;
 }
 
+static u64 next_pow2(u64 v) { u64 p = 1; while (p < v) p <<= 1; return p; }
+
+// k-mer keys, k <= 32: open-addressed hash-count in HBM, then sort only the distinct survivors
+static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
+{
+  kmx_ctx* ctx = ln->ctx;
+  const u32 P = ctx->prm.nb_partitions;
+  double f;
+  { std::lock_guard<std::mutex> g(ctx->mu); f = ctx->ht_factor; }
+  std::vector<u64> toff(P + 1, 0), tcap(P);
+  u64 K = 0, max_cap = 0;
+  for (u32 p = 0; p < P; p++) {
+    tcap[p] = next_pow2(std::max<u64>(1024, (u64)((double)ln->h_kcnt[p] * f) + 1));
+    toff[p + 1] = toff[p] + tcap[p]; K += ln->h_kcnt[p]; max_cap = std::max(max_cap, tcap[p]);
+  }
+  for (u32 p = 0; p < P; p++) ctx->lists[(size_t)sample * P + p] = ListRef();
+  if (K == 0) return KMX_OK;
+  const u64 TS = toff[P];
+  if (TS >= 0xFFFFFFF0ULL) return KMX_HT_FALLBACK;
+  CK(ensure(ln, ln->ht_keys, TS * 8)); CK(ensure(ln, ln->ht_cnts, TS * 4));
+  CK(ensure(ln, ln->keys_lo, TS * 8)); CK(ensure(ln, ln->keys_lo2, TS * 8));
+  // device meta: u64 toff[P] | tcap[P] | oo[P] ; u32 pcnt[P] | overflow
+  const size_t mb = (size_t)P * 24 + (size_t)P * 4 + 64;
+  CK(ensure(ln, ln->tmp_cnt, mb));
+  CK(ensure_pin(ln, mb + (size_t)P * 32 + 256));
+  u64* d_toff = (u64*)ln->tmp_cnt.p; u64* d_tcap = d_toff + P; u64* d_oo = d_tcap + P;
+  u32* d_pcnt = (u32*)(d_oo + P); u32* d_ovf = d_pcnt + P;
+  u64* hp = (u64*)ln->h_pin;
+  memcpy(hp, toff.data(), P * 8); memcpy(hp + P, tcap.data(), P * 8);
+  CK(cudaMemcpyAsync(d_toff, hp, (size_t)P * 16, cudaMemcpyHostToDevice, ln->st));
+  CK(cudaMemsetAsync(d_pcnt, 0, (size_t)P * 4 + 4, ln->st));
+  { PROF(KMX_PROF_FILL);
+    CK(cudaMemsetAsync(ln->ht_keys.p, 0xFF, TS * 8, ln->st));
+    CK(cudaMemsetAsync(ln->ht_cnts.p, 0, TS * 4, ln->st)); }
+  S2Common c; c.W = 1; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
+  c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
+  { PROF(KMX_PROF_EXPAND); CK(launch_ht_insert_records(c, (u64*)ln->ht_keys.p, (u32*)ln->ht_cnts.p, d_toff, d_tcap, d_ovf, ln->st, &ln->launches)); }
+  { PROF(KMX_PROF_RLE); CK(launch_ht_compact(P, max_cap, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap, hard_min,
+                                             (u64*)ln->keys_lo.p, d_pcnt, ln->st, &ln->launches)); }
+  u32* h_pc = (u32*)(ln->h_pin + (size_t)P * 16);
+  CK(cudaMemcpyAsync(h_pc, d_pcnt, (size_t)P * 4 + 4, cudaMemcpyDeviceToHost, ln->st));
+  CK(cudaStreamSynchronize(ln->st));
+  if (h_pc[P]) {                                   // a table filled up: grow the factor, redo this sample on the sort path
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->ht_factor = std::min(4.0, std::max(ctx->ht_factor, f) * 2.0);
+    return KMX_HT_FALLBACK;
+  }
+  std::vector<u32> pcnt(h_pc, h_pc + P);
+  std::vector<u64> sb(P), se(P), oo(P + 1, 0);
+  u32 max_n = 0;
+  for (u32 p = 0; p < P; p++) { sb[p] = toff[p]; se[p] = toff[p] + pcnt[p]; oo[p + 1] = oo[p] + pcnt[p]; max_n = std::max(max_n, pcnt[p]); }
+  const u64 D = oo[P];
+  CK(ensure(ln, ln->sort_work, radix_sort_work_bytes(P, sb.data(), se.data())));
+  int in_alt = 0;
+  { PROF(KMX_PROF_SORT);
+    CK(segmented_radix_sort(P, sb.data(), se.data(), (u64*)ln->keys_lo.p, nullptr, (u64*)ln->keys_lo2.p, nullptr, 1, 0,
+                            2 * (int)ctx->prm.kmer_size, ln->sort_work.p, &in_alt, ln->st, &ln->launches)); }
+  void *kp = nullptr, *cp = nullptr;
+  CK(arena_alloc(ctx, D * 8, &kp));
+  CK(arena_alloc(ctx, D * 4, &cp));
+  memcpy(hp, oo.data(), P * 8);
+  CK(cudaMemcpyAsync(d_oo, hp, (size_t)P * 8, cudaMemcpyHostToDevice, ln->st));
+  { PROF(KMX_PROF_RLE);
+    CK(launch_ht_lookup(P, max_n, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap,
+                        (const u64*)(in_alt ? ln->keys_lo2.p : ln->keys_lo.p), d_toff, d_pcnt, d_oo, (u64*)kp, (u32*)cp, ln->st, &ln->launches)); }
+  CK(cudaStreamSynchronize(ln->st));               // pinned staging is reused by the next call
+  for (u32 p = 0; p < P; p++) {
+    ListRef& L = ctx->lists[(size_t)sample * P + p];
+    L.lo = (u64*)kp + oo[p]; L.hi = nullptr; L.cnt = (u32*)cp + oo[p]; L.n = pcnt[p];
+  }
+  return KMX_OK;
+}
+
 static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp, kmx_merge_result* res,
                         const std::vector<MergeList>& hl, u64 max_n, u64 tot_n)
 {
@@ -65,7 +138,39 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
   if (res) *res = ctx->last_res;
   if (tot_n == 0) return KMX_OK;
   if (tot_n >= 0xFFFFFFF0ULL) return fail(ln, KMX_ERR_ARG, "partition %u holds %llu (key,sample) entries (>= 2^32)", partition, (unsigned long long)tot_n);
-  // 1. union of keys: concatenate, sort, unique
+  // 1. union of keys.  k <= 32: open-addressed hash SET of all N lists' keys, then sort only the distinct
+  //    keys; otherwise (or if the set overflows): concatenate, sort, unique
+  u64* ulo = nullptr; u64* uhi = nullptr; u64 nu = 0;
+  bool have_union = false;
+  if (KW == 1 && ctx->ht_union_ok) {
+    const u64 cap = next_pow2(std::max<u64>(4096, (u64)(2.5 * (double)max_n)));
+    if (cap < 0x7FFFFFFFULL) {
+      CK(ensure(ln, ctx->uni_lo2, cap * 8));                         // table
+      CK(ensure(ln, ctx->uni_lo, cap * 8));                          // distinct keys, unordered
+      CK(ensure(ln, ln->keys_lo, cap * 8)); CK(ensure(ln, ln->keys_lo2, cap * 8));
+      CK(ensure(ln, ln->tmp_cnt, 64));
+      u32* d_cnt = (u32*)ln->tmp_cnt.p; u32* d_ovf = d_cnt + 1;
+      CK(cudaMemsetAsync(d_cnt, 0, 8, ln->st));
+      CK(cudaMemsetAsync(ctx->uni_lo2.p, 0xFF, cap * 8, ln->st));
+      CK(launch_ht_union((const MergeList*)ctx->d_lists.p, N, max_n, (u64*)ctx->uni_lo2.p, nullptr, cap, d_ovf, (u64*)ln->keys_lo.p, d_cnt, ln->st, &ln->launches));
+      u32* hres = (u32*)ln->h_pin;                                   // lists/soft staging was consumed by the H2D copies above
+      CK(cudaStreamSynchronize(ln->st));
+      CK(cudaMemcpyAsync(hres, d_cnt, 8, cudaMemcpyDeviceToHost, ln->st));
+      CK(cudaStreamSynchronize(ln->st));
+      if (!hres[1]) {
+        nu = hres[0];
+        u64 seg1[2] = {0, nu};
+        CK(ensure(ln, ln->sort_work, radix_sort_work_bytes(1, seg1)));
+        int alt = 0;
+        CK(segmented_radix_sort(1, seg1, nullptr, (u64*)ln->keys_lo.p, nullptr, (u64*)ln->keys_lo2.p, nullptr, 1, 0,
+                                hash ? bit_length(ctx->prm.window_bits * ctx->prm.nb_partitions - 1) : 2 * (int)ctx->prm.kmer_size,
+                                ln->sort_work.p, &alt, ln->st, &ln->launches));
+        ulo = (u64*)(alt ? ln->keys_lo2.p : ln->keys_lo.p);
+        have_union = true;
+      }
+    }
+  }
+  if (!have_union) {
   CK(ensure(ln, ctx->uni_lo, tot_n * 8)); CK(ensure(ln, ctx->uni_lo2, tot_n * 8));
   if (KW == 2) { CK(ensure(ln, ctx->uni_hi, tot_n * 8)); CK(ensure(ln, ctx->uni_hi2, tot_n * 8)); }
   u64 o = 0;
@@ -79,18 +184,19 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
   CK(ensure(ln, ln->sort_work, wb));
   const int end_bit = hash ? bit_length(ctx->prm.window_bits * ctx->prm.nb_partitions - 1) : 2 * (int)ctx->prm.kmer_size;
   int in_alt = 0;
-  CK(segmented_radix_sort(1, seg, (u64*)ctx->uni_lo.p, (u64*)ctx->uni_hi.p, (u64*)ctx->uni_lo2.p, (u64*)ctx->uni_hi2.p,
+  CK(segmented_radix_sort(1, seg, nullptr, (u64*)ctx->uni_lo.p, (u64*)ctx->uni_hi.p, (u64*)ctx->uni_lo2.p, (u64*)ctx->uni_hi2.p,
                           KW, 0, end_bit, ln->sort_work.p, &in_alt, ln->st, &ln->launches));
   const u64* slo = (const u64*)(in_alt ? ctx->uni_lo2.p : ctx->uni_lo.p);
   const u64* shi = (const u64*)(in_alt ? ctx->uni_hi2.p : ctx->uni_hi.p);
   std::vector<u64> toff, soff;
   CK(rle_segments(1, seg, slo, shi, KW, 1, ln->sort_work.p, toff, soff, 0, nullptr, nullptr, nullptr, ln->st, &ln->launches));
-  const u64 nu = soff[1];
+  nu = soff[1];
   CK(ensure(ln, ln->keys_lo, nu * 8));
   if (KW == 2) CK(ensure(ln, ln->keys_hi, nu * 8));
   CK(ensure(ln, ln->tmp_cnt, nu * 4 + 64));
-  u64* ulo = (u64*)ln->keys_lo.p; u64* uhi = KW == 2 ? (u64*)ln->keys_hi.p : nullptr;
+  ulo = (u64*)ln->keys_lo.p; uhi = KW == 2 ? (u64*)ln->keys_hi.p : nullptr;
   CK(rle_segments(1, seg, slo, shi, KW, 1, ln->sort_work.p, toff, soff, 1, ulo, uhi, (u32*)ln->tmp_cnt.p, ln->st, &ln->launches));
+  }
   // 2. solid_in per row, keep flags, output row numbers
   CK(ensure(ln, ctx->solid_in, nu * 4)); CK(ensure(ln, ctx->keep, nu * 4)); CK(ensure(ln, ctx->out_row, nu * 4 + 16));
   CK(ensure(ln, ctx->scan_work, scan_u32_work_bytes(nu)));

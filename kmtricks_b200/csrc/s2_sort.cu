@@ -169,7 +169,7 @@ static constexpr int RS_THREADS = 256;
 static constexpr int RS_ITEMS = 16;
 static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 4096
 
-struct RsTile { u64 begin; u32 len; u32 dstride; u64 cbase; };   // cbase: index of (tile, digit 0) in counts
+struct RsTile { u64 begin; u32 len; u32 dstride; u64 cbase; u64 adj; };   // cbase: index of (tile, digit 0) in counts; adj = segment begin - keys in earlier segments
 
 __device__ __forceinline__ u32 rs_digit(u64 lo, u64 hi, int shift, u32 mask)
 {
@@ -199,7 +199,7 @@ template <int W>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const RsTile* __restrict__ tiles, const u64* __restrict__ lo, const u64* __restrict__ hi,
                   u64* __restrict__ olo, u64* __restrict__ ohi, int shift, u32 mask,
-                  const u32* __restrict__ scanned, u64 off0)
+                  const u32* __restrict__ scanned)
 {
   __shared__ u32 s_wcnt[RS_THREADS / 32][256];
   __shared__ u32 s_gpos[256];
@@ -242,7 +242,7 @@ rs_scatter_kernel(const RsTile* __restrict__ tiles, const u64* __restrict__ lo, 
   for (int i = 0; i < RS_ITEMS; i++) {
     const u32 d = dg[i];
     if (d < 256) {
-      u64 pos = off0 + s_gpos[d] + s_wcnt[w][d] + rk[i];
+      u64 pos = t.adj + s_gpos[d] + s_wcnt[w][d] + rk[i];
       olo[pos] = kl[i];
       if (W == 2) ohi[pos] = kh[i];
     }
@@ -251,16 +251,17 @@ rs_scatter_kernel(const RsTile* __restrict__ tiles, const u64* __restrict__ lo, 
 
 // Host: build the tile table for segments [h_seg_off[i], h_seg_off[i+1]).
 // Work buffer layout: [RsTile ntiles][u32 counts 256*ntiles][scan work]
-static u64 rs_count_tiles(u32 nseg, const u64* so)
+// Segments: [so[s], se ? se[s] : so[s+1]).  With explicit ends the segments may have gaps.
+static u64 rs_count_tiles(u32 nseg, const u64* so, const u64* se = nullptr)
 {
   u64 nt = 0;
-  for (u32 s = 0; s < nseg; s++) nt += (so[s + 1] - so[s] + RS_TILE - 1) / RS_TILE;
+  for (u32 s = 0; s < nseg; s++) nt += ((se ? se[s] : so[s + 1]) - so[s] + RS_TILE - 1) / RS_TILE;
   return nt;
 }
 
-size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off)
+size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off, const u64* h_seg_end)
 {
-  u64 nt = rs_count_tiles(nseg, h_seg_off);
+  u64 nt = rs_count_tiles(nseg, h_seg_off, h_seg_end);
   size_t a = (size_t)nt * sizeof(RsTile);
   a = (a + 255) & ~(size_t)255;
   size_t b = (size_t)nt * 256 * 4;
@@ -268,27 +269,28 @@ size_t radix_sort_work_bytes(u32 nseg, const u64* h_seg_off)
   return a + b + scan_u32_work_bytes(nt * 256) + 256;
 }
 
-cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, u64* lo, u64* hi, u64* lo_alt, u64* hi_alt,
+cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, const u64* h_seg_end, u64* lo, u64* hi, u64* lo_alt, u64* hi_alt,
                                  int W, int begin_bit, int end_bit, void* d_work, int* result_in_alt,
                                  cudaStream_t st, u64* launches)
 {
   *result_in_alt = 0;
-  const u64 nt = rs_count_tiles(nseg, h_seg_off);
+  const u64 nt = rs_count_tiles(nseg, h_seg_off, h_seg_end);
   if (nt == 0 || end_bit <= begin_bit) return cudaSuccess;
-  const u64 total = h_seg_off[nseg] - h_seg_off[0];
+  u64 total = 0;
+  for (u32 s = 0; s < nseg; s++) total += (h_seg_end ? h_seg_end[s] : h_seg_off[s + 1]) - h_seg_off[s];
   if (total >= 0xFFFFFFFFULL) return cudaErrorInvalidValue;
   static thread_local RsTile* h_tiles = nullptr; static thread_local u64 h_cap = 0;
   if (h_cap < nt) { if (h_tiles) cudaFreeHost(h_tiles); cudaError_t e = cudaMallocHost((void**)&h_tiles, nt * sizeof(RsTile)); if (e != cudaSuccess) { h_tiles = nullptr; h_cap = 0; return e; } h_cap = nt; }
-  u64 ti = 0;
+  u64 ti = 0, before = 0;
   for (u32 s = 0; s < nseg; s++) {
-    u64 b = h_seg_off[s], e = h_seg_off[s + 1];
+    u64 b = h_seg_off[s], e = h_seg_end ? h_seg_end[s] : h_seg_off[s + 1];
     u64 n = (e - b + RS_TILE - 1) / RS_TILE;
     for (u64 j = 0; j < n; j++) {
       RsTile& t = h_tiles[ti + j];
       t.begin = b + j * RS_TILE; t.len = (u32)std::min<u64>(RS_TILE, e - t.begin);
-      t.dstride = (u32)n; t.cbase = ti * 256 + j;
+      t.dstride = (u32)n; t.cbase = ti * 256 + j; t.adj = b - before;
     }
-    ti += n;
+    ti += n; before += e - b;
   }
   char* wp = (char*)d_work;
   RsTile* d_tiles = (RsTile*)wp; wp += ((size_t)nt * sizeof(RsTile) + 255) & ~(size_t)255;
@@ -305,8 +307,8 @@ cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, u64* lo, u64* h
     *launches += 1;
     e = scan_u32_inplace(d_counts, nt * 256, nullptr, d_scanw, st, launches);
     if (e != cudaSuccess) return e;
-    if (W == 1) rs_scatter_kernel<1><<<(unsigned)nt, RS_THREADS, 0, st>>>(d_tiles, cl, ch, al, ah, shift, mask, d_counts, h_seg_off[0]);
-    else rs_scatter_kernel<2><<<(unsigned)nt, RS_THREADS, 0, st>>>(d_tiles, cl, ch, al, ah, shift, mask, d_counts, h_seg_off[0]);
+    if (W == 1) rs_scatter_kernel<1><<<(unsigned)nt, RS_THREADS, 0, st>>>(d_tiles, cl, ch, al, ah, shift, mask, d_counts);
+    else rs_scatter_kernel<2><<<(unsigned)nt, RS_THREADS, 0, st>>>(d_tiles, cl, ch, al, ah, shift, mask, d_counts);
     *launches += 1;
     std::swap(cl, al); std::swap(ch, ah);
     *result_in_alt ^= 1;
@@ -429,7 +431,7 @@ cudaError_t rle_segments(u32 nseg, const u64* h_seg_off, const u64* lo, const u6
       u64 n = (e - b + RS_TILE - 1) / RS_TILE;
       for (u64 j = 0; j < n; j++) {
         RsTile& t = tiles[ti + j];
-        t.begin = b + j * RS_TILE; t.len = (u32)std::min<u64>(RS_TILE, e - t.begin); t.dstride = 0; t.cbase = 0;
+        t.begin = b + j * RS_TILE; t.len = (u32)std::min<u64>(RS_TILE, e - t.begin); t.dstride = 0; t.cbase = 0; t.adj = 0;
         sb[ti + j] = b; se[ti + j] = e;
       }
       ti += n;

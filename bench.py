@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4, help="samples in flight (kmx_run_samples lanes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-samples", type=int, default=4, help="samples in the bounded CPU-reference run")
+    ap.add_argument("--ref-samples", type=int, default=8, help="samples in the bounded CPU-reference run")
     ap.add_argument("--ref-reads", type=int, default=250_000)
     return ap.parse_args()
 
@@ -138,6 +138,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.mode}
 
 
+def workload_name(args, world=1):
+    return (f"cfg2: {args.samples} samples x {args.reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
+            f"P={args.partitions}, bloom={args.bloom_size}, hard-min {args.hard_min}, --static-repart, m=10"
+            + (f"; samples per GPU (x{world} GPUs = {args.samples * world} columns), partitions sharded over GPUs, "
+               f"one NCCL all-to-all-v of bucket regions per sample" if world > 1 else ""))
+
+
 def n_kmers(args):
     return args.samples * args.reads * (args.read_len - args.kmer_size + 1)
 
@@ -161,17 +168,25 @@ def run_reference_once(args, workdir, threads):
     return dt, args.ref_samples * args.ref_reads * (args.read_len - args.kmer_size + 1)
 
 
-def make_ref_inputs(args, workdir):
+def _write_ref_sample(job):
     from kmtricks_b200 import synth
+    path, s, reads, read_len, genome = job
+    with open(path, "wb") as g:
+        step = 50_000
+        for r0 in range(0, reads, step):
+            g.write(synth.make_fastq(1234, s, min(step, reads - r0), L=read_len, G=genome, d=2e-3, e=2e-3, revcomp=True, first_read=r0))
+    return path
+
+
+def make_ref_inputs(args, workdir):
+    """Same generator as the GPU arm (numpy twin of kmx_synth_fastq), one worker process per sample."""
+    import multiprocessing as mp
+    jobs = [(os.path.join(workdir, f"S{s}.fastq"), s, args.ref_reads, args.read_len, args.genome) for s in range(args.ref_samples)]
+    with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        pool.map(_write_ref_sample, jobs)
     with open(os.path.join(workdir, "fof.txt"), "w") as f:
-        for s in range(args.ref_samples):
-            p = os.path.join(workdir, f"S{s}.fastq")
-            with open(p, "wb") as g:
-                step = 50_000
-                for r0 in range(0, args.ref_reads, step):
-                    g.write(synth.make_fastq(1234, s, min(step, args.ref_reads - r0), L=args.read_len, G=args.genome,
-                                             d=2e-3, e=2e-3, revcomp=True, first_read=r0))
-            f.write(f"S{s}: {p}\n")
+        for s, j in enumerate(jobs):
+            f.write(f"S{s}: {j[0]}\n")
 
 
 def ref_workdir():
@@ -200,8 +215,8 @@ def main_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    cfg = {"workload": f"cfg2-bounded: {args.ref_samples} samples x {args.ref_reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
-                       f"P={args.partitions}, bloom={args.bloom_size}, hard-min {args.hard_min} (bounded sample of {args.samples} x {args.reads})",
+    cfg = {"workload": workload_name(args, int(os.environ.get("WORLD_SIZE", "1"))),
+           "sample": f"each step = {args.ref_samples} samples x {args.ref_reads} reads of that workload's generator (bounded so the run ends in minutes)",
            "l2": "inputs larger than L2"}
     if not O.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/kmtricks not built (run oracle/build_ref.sh where /root/reference exists)"}))
@@ -400,8 +415,16 @@ def main_kmx(args):
             alg = body_sum[0] / max(len(my_parts), 1)
             what = "S3/S4: matrix body written"
         ach = alg / (dur_ms * 1e-3) / 1e9
+        traffic = None
+        try:      # dram__bytes_read+write per launch from the committed ncu --set full capture (same launch shape only)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+            key = {"s1_superk": "s1_superk", "hash_hist": "hash_hist_kernel", "hash_emit": "hash_emit_kernel", "fq_index": "fq_index_lines"}.get(top)
+            if key in tr and args.reads == 1_000_000 and args.read_len == 150 and args.mode == "hash:bf:bin" and args.partitions == 64 and args.bloom_size == 200_000_000:
+                traffic = tr[key]["dram_read_bytes"] + tr[key]["dram_write_bytes"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg, "launch_ms": dur_ms, "what": what, "peak_source": peak_src}
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": dur_ms, "what": what, "peak_source": peak_src}
 
     # ---- end to end through host buffers (pinned FASTQ in, bodies out)
     e2e = None
@@ -447,10 +470,7 @@ def main_kmx(args):
         line = {"metric": "k-mers/s end-to-end (repart->merge)", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": f"cfg2: {N} samples x {args.reads} reads x {args.read_len} nt, k={args.kmer_size}, {args.mode}, "
-                                       f"P={P}, bloom={args.bloom_size}, hard-min {args.hard_min}, --static-repart, m=10"
-                                       + (f"; samples per GPU (x{world} GPUs = {N_tot} columns), partitions sharded over GPUs, "
-                                          f"one NCCL all-to-all-v of bucket regions per sample" if world > 1 else ""),
+                "config": {"workload": workload_name(args, world),
                            "kmers_per_step": kmers_step, "l2": "inputs larger than L2 (315 MB text per launch)",
                            "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM", "lanes": args.lanes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

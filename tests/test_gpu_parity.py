@@ -68,3 +68,17 @@ def test_pipeline_parity_edge_cases(name, edge_samples):
 def test_per_sample_hard_min_override(synth_samples):
     got, want = _run_both(synth_samples, CASES["kmer_count"], {1: 1, 3: 4})
     _compare(got, want, CASES["kmer_count"]["P"], len(synth_samples))
+
+
+@pytest.mark.parametrize("name,case,N", [
+    ("cfg3_shape", dict(k=31, P=512, mode="kmer:count:bin", hard_min=1, soft_min=2, recurrence_min=2), 130),
+    ("cfg5_shape", dict(k=63, P=256, mode="kmer:pa:bin", hard_min=1, soft_min=3, share_min=2, recurrence_min=1), 70),
+    ("cfg4_shape", dict(k=31, P=512, mode="hash:bft:bin", hard_min=1, soft_min=2, share_min=3, bloom_size=100_000), 130),
+])
+def test_many_samples_many_partitions(name, case, N):
+    """The shapes of BASELINE configs 3-5 (hundreds of samples, P = 256/512, count / pa+rescue / bft)
+    at a size the oracle finishes in seconds: N not a multiple of 8, most (sample, partition) lists tiny."""
+    from kmtricks_b200 import synth
+    samples = [[synth.make_fastq(3, s, 120, L=150, G=6000, d=1e-2, e=5e-3, revcomp=True)] for s in range(N)]
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], N)

@@ -80,6 +80,7 @@ struct Lane {
   char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
   DBuf hist, sub_counts, sub_off;
+  u64 d_est = 0;                   // expected surviving (key,count) pairs per sample (grows with what was seen)
   DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt, ht_keys, ht_cnts;
   // ---- profiling
   std::vector<ProfSpan> prof_spans;
@@ -96,6 +97,7 @@ struct kmx_ctx {
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
+  int active_lanes = 1;            // lanes running concurrently (sizes the L2-resident histogram groups)
   double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
   bool ht_union_ok = true;
   bool prof_on = false;
@@ -528,54 +530,80 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min);
 static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min);
 static const int KMX_HT_FALLBACK = -1000;   // internal: table overflowed, use the sort path
 
-// win_sample / win_part (host, [P], optional): window v of the histogram holds partition win_part[v] of
-// sample slot win_sample[v] (multi-GPU: one pass counts the same partitions of several samples)
+// Hash keys, histogram path.  Partitions are processed in GROUPS of `gp` windows whose histogram
+// (gp x W x u32, <= 32 MB) is reused group after group and therefore stays L2-resident: fill (RED),
+// count survivors per sub-chunk, device-side scan + bump allocation of the output space, ordered
+// emit + re-zero -- no DRAM streaming of a P x W histogram and no host round trip per group.
+// win_sample / win_part (host, [P], optional): window v holds partition win_part[v] of sample slot
+// win_sample[v] (multi-GPU: one pass counts the same partitions of several samples).
 static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u32* win_sample = nullptr, const u32* win_part = nullptr)
 {
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   const u64 Wb = ctx->prm.window_bits;
   const u32 S = (u32)((Wb + HIST_SUB - 1) / HIST_SUB);
-  const size_t hist_bytes = (size_t)P * Wb * 4;
+  // up to 1 GiB of histogram per lane: all partitions in one group (fewest launches, measured fastest);
+  // beyond that (big Bloom filters) groups of ~100 MB per in-flight lane, reused group after group
+  u32 gp = P;
+  if ((u64)P * Wb * 4 > ((u64)1 << 30)) {
+    const u64 budget = ((u64)100 << 20) / (u64)std::max(1, ctx->active_lanes);
+    gp = (u32)std::max<u64>(1, std::min<u64>(P, budget / (Wb * 4)));
+  }
+  const size_t hist_bytes = (size_t)gp * Wb * 4;
   if (ln->hist.cap < hist_bytes) {
     CK(ensure(ln, ln->hist, hist_bytes));
     CK(cudaMemsetAsync(ln->hist.p, 0, ln->hist.cap, ln->st));
   }
-  CK(ensure(ln, ln->sub_counts, (size_t)P * S * 4));
-  CK(ensure(ln, ln->sub_off, ((size_t)P * S + 1) * 8));
-  CK(ensure_pin(ln, ((size_t)P * S + 1) * 8 + (size_t)P * 32 + 256));
+  // device meta: sub_counts u32[P*S] | sub_off u64[P*S] | list_off u64[P] | list_n u64[P] | meta u64[2] | flags u32[2] | win_part u32[P]
+  const size_t n_sub = (size_t)P * S;
+  CK(ensure(ln, ln->sub_counts, n_sub * 4));
+  CK(ensure(ln, ln->sub_off, n_sub * 8 + (size_t)P * 16 + 16 + 8 + (size_t)P * 4 + 64));
+  u64* d_sub_off = (u64*)ln->sub_off.p; u64* d_loff = d_sub_off + n_sub; u64* d_ln = d_loff + P; u64* d_meta = d_ln + P;
+  u32* d_flags = (u32*)(d_meta + 2); u32* d_wpart = d_flags + 2;
+  CK(ensure_pin(ln, (size_t)P * 16 + 32 + (size_t)P * 32 + 256));
   S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
   c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   u64 mlo, mhi; fastmod_magic(Wb, mlo, mhi);
-  { PROF(KMX_PROF_HASH_HIST); CK(launch_hash_hist(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, (u32*)ln->sub_counts.p, S, ln->st, &ln->launches)); }
-  u64* so = (u64*)ln->sub_off.p;
-  CK(launch_scan_u32((const u32*)ln->sub_counts.p, so, (u64)P * S, so + (u64)P * S, ln->st, &ln->launches));
-  u64* h_so = (u64*)ln->h_pin;
-  CK(cudaMemcpyAsync(h_so, so, ((size_t)P * S + 1) * 8, cudaMemcpyDeviceToHost, ln->st));
-  CK(cudaStreamSynchronize(ln->st));
-  const u64 D = h_so[(size_t)P * S];
-  void* kp = nullptr; void* cp = nullptr;
-  CK(arena_alloc(ctx, D * 8, &kp));
-  CK(arena_alloc(ctx, D * 4, &cp));
-  const u32* d_wpart = nullptr;
+  const u32* dwp = nullptr;
   if (win_part) {
-    CK(ensure(ln, ln->tmp_cnt, (size_t)P * 4 + 64));
-    // h_so was consumed above (D) but is still needed below: stage the map behind it
-    u32* hp = (u32*)(ln->h_pin + ((size_t)P * S + 1) * 8);
+    u32* hp = (u32*)(ln->h_pin + (size_t)P * 16 + 32);
     memcpy(hp, win_part, (size_t)P * 4);
-    CK(cudaMemcpyAsync(ln->tmp_cnt.p, hp, (size_t)P * 4, cudaMemcpyHostToDevice, ln->st));
-    d_wpart = (const u32*)ln->tmp_cnt.p;
+    CK(cudaMemcpyAsync(d_wpart, hp, (size_t)P * 4, cudaMemcpyHostToDevice, ln->st));
+    dwp = d_wpart;
   }
-  { PROF(KMX_PROF_HASH_EMIT); CK(launch_hash_emit(P, Wb, S, (u32*)ln->hist.p, hard_min, so, (u64*)kp, (u32*)cp, ln->d_cursor, d_wpart, ln->st, &ln->launches)); }
-  for (u32 v = 0; v < P; v++) {
-    u64 b = h_so[(size_t)v * S], e = h_so[(size_t)(v + 1) * S];
-    if (win_part && ln->h_cursor[v] == 0) continue;       // unused window
-    const u32 smp = win_sample ? win_sample[v] : sample, prt = win_part ? win_part[v] : v;
-    ListRef& L = ctx->lists[(size_t)smp * P + prt];
-    L.lo = (u64*)kp + b; L.hi = nullptr; L.cnt = (u32*)cp + b; L.n = e - b;
+  u64 cap = std::max<u64>(4096, ln->d_est);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    void* kp = nullptr; void* cp = nullptr;
+    CK(arena_alloc(ctx, cap * 8, &kp));
+    CK(arena_alloc(ctx, cap * 4, &cp));
+    u64* hm = (u64*)(ln->h_pin + (size_t)P * 16);            // staging for meta = {cursor 0, capacity}
+    hm[0] = 0; hm[1] = cap; hm[2] = 0;
+    CK(cudaMemcpyAsync(d_meta, hm, 24, cudaMemcpyHostToDevice, ln->st));    // meta[2] + flags[2]
+    for (u32 p0 = 0; p0 < P; p0 += gp) {
+      const u32 g = std::min(gp, P - p0);
+      { PROF(KMX_PROF_HASH_HIST);
+        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, S, p0, g, (u32*)ln->sub_counts.p, d_sub_off, d_loff, d_ln,
+                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 0)); }
+      { PROF(KMX_PROF_HASH_EMIT);
+        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, S, p0, g, (u32*)ln->sub_counts.p, d_sub_off, d_loff, d_ln,
+                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 1)); }
+    }
+    u64* h_l = (u64*)ln->h_pin;                               // list_off[P] | list_n[P] then meta/flags
+    CK(cudaMemcpyAsync(h_l, d_loff, (size_t)P * 16 + 24, cudaMemcpyDeviceToHost, ln->st));
+    CK(cudaStreamSynchronize(ln->st));
+    const u64 D = h_l[2 * P];
+    const u32 ovf = *(u32*)(h_l + 2 * P + 2);
+    ln->d_est = std::max<u64>(ln->d_est, D + D / 4 + 1024);
+    if (ovf) { cap = D + 1024; continue; }                   // the cursor kept counting: exact size now known, histogram is all-zero again
+    for (u32 v = 0; v < P; v++) {
+      if (win_part && ln->h_cursor[v] == 0) continue;       // unused window
+      const u32 smp = win_sample ? win_sample[v] : sample, prt = win_part ? win_part[v] : v;
+      ListRef& L = ctx->lists[(size_t)smp * P + prt];
+      L.lo = (u64*)kp + h_l[v]; L.hi = nullptr; L.cnt = (u32*)cp + h_l[v]; L.n = ln->h_cursor[v] ? h_l[P + v] : 0;
+    }
+    return KMX_OK;
   }
-  if (win_part) CK(cudaStreamSynchronize(ln->st));        // pinned map staging is reused
-  return KMX_OK;
+  return fail(ln, KMX_ERR_CUDA, "hash-count output space overflowed twice");
 }
 
 static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
@@ -591,7 +619,8 @@ static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
       if (ctx->hist_ok < 0) {                      // decide once: histogram path if it fits comfortably
         size_t free_b = 0, tot_b = 0;
         cudaMemGetInfo(&free_b, &tot_b);
-        ctx->hist_ok = hist_bytes < (free_b / 8) ? 1 : 0;
+        (void)hist_bytes;
+        ctx->hist_ok = ctx->prm.window_bits * 4 < (free_b / 8) ? 1 : 0;   // one window must fit comfortably
       }
       ok = ctx->hist_ok;
     }
@@ -625,9 +654,11 @@ extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* text
       size_t free_b = 0, tot_b = 0;
       CK(cudaMemGetInfo(&free_b, &tot_b));
       size_t hist_bytes = (size_t)P * ctx->prm.window_bits * 4;
-      ctx->hist_ok = hist_bytes * nlanes < (free_b / 4) ? 1 : 0;
+      (void)hist_bytes;
+      ctx->hist_ok = ctx->prm.window_bits * 4 * nlanes < (free_b / 4) ? 1 : 0;
     }
   }
+  ctx->active_lanes = (int)nlanes;
   std::atomic<int> first_err(0);
   auto work = [&](u32 t) {
     cudaSetDevice(ctx->device);
@@ -648,6 +679,7 @@ extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* text
     for (u32 t = 0; t < nlanes; t++) th.emplace_back(work, t);
     for (auto& x : th) x.join();
   }
+  ctx->active_lanes = 1;
   return first_err.load();
 }
 

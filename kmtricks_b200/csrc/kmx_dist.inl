@@ -198,9 +198,10 @@ extern "C" int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* 
     if (ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok < 0) {
       size_t free_b = 0, tot_b = 0;
       CK(cudaMemGetInfo(&free_b, &tot_b));
-      ctx->hist_ok = (size_t)P * ctx->prm.window_bits * 4 * nlanes < (free_b / 4) ? 1 : 0;
+      ctx->hist_ok = (size_t)ctx->prm.window_bits * 4 * nlanes < (free_b / 4) ? 1 : 0;
     }
   }
+  ctx->active_lanes = (int)nlanes;
   std::atomic<int> first_err(0);
   auto work = [&](u32 t) {
     cudaSetDevice(ctx->device);

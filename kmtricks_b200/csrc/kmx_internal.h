@@ -50,12 +50,12 @@ struct S2Common {
 };
 
 // hash mode, histogram path
-static const u32 HIST_SUB = 65536;   // slots per sub-chunk
-cudaError_t launch_hash_hist(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi,
-                             u32* hist /* P*Wbits */, u32 hard_min, u32* sub_counts /* P*S */, u32 S,
-                             cudaStream_t st, u64* launches);
-cudaError_t launch_hash_emit(u32 P, u64 Wbits, u32 S, u32* hist, u32 hard_min, const u64* sub_off,
-                             u64* out_keys, u32* out_counts, const u32* bcnt, const u32* win_part, cudaStream_t st, u64* launches);
+static const u32 HIST_SUB = 8192;    // slots per sub-chunk (one CTA of the sweep kernels)
+// hash keys, histogram path: partitions are processed in groups of gp windows that stay L2-resident
+// (phase 0: fill + count survivors per 64K sub-chunk; phase 1: device-side scan/allocation + ordered emit + re-zero)
+cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi, u32* hist, u32 hard_min,
+                              u32 S, u32 p0, u32 gp, u32* sub_counts, u64* sub_off, u64* list_off, u64* list_n, u64* meta, u32* flags,
+                              u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase);
 cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
 
 // generic path: expand -> keys, segmented radix sort, run-length

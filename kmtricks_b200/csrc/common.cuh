@@ -78,22 +78,16 @@ __device__ __forceinline__ u64 fastmod64(u64 x, const FastMod64& f)
   return p_hi + (s < p_lo ? 1ULL : 0ULL);
 }
 
-// exact x % d for d < 2^32 (the usual case: a partition's window has < 2^32 slots):
-// two Barrett steps on 32-bit limbs.  m64 = floor(2^64 / d) (d >= 2), host-computed.
+// exact x % d for 2 <= d < 2^31 (the usual case: a partition's window has far fewer slots):
+// one Barrett step.  m64 = floor((2^64-1) / d), host-computed.  q = floor(x*m64 / 2^64) is the
+// true quotient or one less (x*m64/2^64 > x/d - 1), so r = x - q*d < 2d < 2^32 and the 32-bit
+// arithmetic below is exact; min(r, r-d) is the conditional subtract (r-d wraps when r < d).
 struct FastMod32 { u32 d; u64 m64; };
 __device__ __forceinline__ u32 fastmod64_d32(u64 x, const FastMod32& f)
 {
-  // step 1: r1 = hi % d   (hi < 2^32): q ~ floor(hi * m64 / 2^64), off by at most 1
-  const u32 hi = (u32)(x >> 32), lo = (u32)x;
-  u32 q1 = (u32)__umul64hi((u64)hi, f.m64);
-  u32 r1 = hi - q1 * f.d;
-  if (r1 >= f.d) r1 -= f.d;
-  // step 2: num = r1 * 2^32 + lo < d * 2^32, quotient < 2^32
-  const u64 num = ((u64)r1 << 32) | lo;
-  u64 q2 = __umul64hi(num, f.m64);
-  u64 r2 = num - q2 * f.d;
-  if (r2 >= f.d) r2 -= f.d;
-  return (u32)r2;
+  const u32 q = (u32)__umul64hi(x, f.m64);
+  const u32 r = (u32)x - q * f.d;
+  return min(r, r - f.d);
 }
 
 // ---- super-k-mer bucket record (own format; SURVEY F6 allows any) -----------------------

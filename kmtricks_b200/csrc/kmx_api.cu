@@ -79,7 +79,7 @@ struct Lane {
   bool in_sample = false, sample_ready = false;
   char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
-  DBuf hist, sub_counts, sub_off;
+  DBuf hist, sub_counts, sub_off, bitmap;
   u64 d_est = 0;                   // expected surviving (key,count) pairs per sample (grows with what was seen)
   DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt, ht_keys, ht_cnts;
   // ---- profiling
@@ -233,7 +233,7 @@ static void lane_destroy(Lane* ln)
   kmx_ctx* ctx = ln->ctx;
   if (ln->st) cudaStreamSynchronize(ln->st);
   DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->records, &ln->hist,
-                  &ln->sub_counts, &ln->sub_off, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
+                  &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
   for (void* p : singles) if (p) cudaFree(p);
@@ -541,7 +541,6 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
   const u64 Wb = ctx->prm.window_bits;
-  const u32 S = (u32)((Wb + HIST_SUB - 1) / HIST_SUB);
   // up to 1 GiB of histogram per lane: all partitions in one group (fewest launches, measured fastest);
   // beyond that (big Bloom filters) groups of ~100 MB per in-flight lane, reused group after group
   u32 gp = P;
@@ -554,19 +553,23 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     CK(ensure(ln, ln->hist, hist_bytes));
     CK(cudaMemsetAsync(ln->hist.p, 0, ln->hist.cap, ln->st));
   }
-  // device meta: sub_counts u32[P*S] | sub_off u64[P*S] | list_off u64[P] | list_n u64[P] | meta u64[2] | flags u32[2] | win_part u32[P]
-  const size_t n_sub = (size_t)P * S;
-  CK(ensure(ln, ln->sub_counts, n_sub * 4));
-  CK(ensure(ln, ln->sub_off, n_sub * 8 + (size_t)P * 16 + 16 + 8 + (size_t)P * 4 + 64));
-  u64* d_sub_off = (u64*)ln->sub_off.p; u64* d_loff = d_sub_off + n_sub; u64* d_ln = d_loff + P; u64* d_meta = d_ln + P;
-  u32* d_flags = (u32*)(d_meta + 2); u32* d_wpart = d_flags + 2;
-  CK(ensure_pin(ln, (size_t)P * 16 + 32 + (size_t)P * 32 + 256));
+  // device meta: chunk_counts u32[gp*CW] | slice_counts u32[gp*CW*8] ; chunk_off u64[gp*CW] | list_off u64[P] | meta u64[4] |
+  // flags u32[2] | win_part u32[P] ; staging: one (u16 slot offset, u32 count) entry per slot of the group (runs per 1024-slot slice)
+  const size_t n_chunks = (size_t)gp * hash_sweep_chunks_per_window(Wb);
+  CK(ensure(ln, ln->sub_counts, n_chunks * 4 * 9));
+  CK(ensure(ln, ln->sub_off, n_chunks * 8 + (size_t)P * 8 + 32 + 8 + (size_t)P * 4 + 64));
+  CK(ensure(ln, ln->bitmap, n_chunks * HIST_SUB * 6));
+  SweepStage stage; stage.cnt = (u32*)ln->bitmap.p; stage.idx = (uint16_t*)(stage.cnt + n_chunks * HIST_SUB);
+  stage.slice_counts = (u32*)ln->sub_counts.p + n_chunks;
+  u64* d_coff = (u64*)ln->sub_off.p; u64* d_loff = d_coff + n_chunks; u64* d_meta = d_loff + P;
+  u32* d_flags = (u32*)(d_meta + 4); u32* d_wpart = d_flags + 2;
+  CK(ensure_pin(ln, (size_t)P * 8 + 64 + (size_t)P * 32 + 256));
   S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
   c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   u64 mlo, mhi; fastmod_magic(Wb, mlo, mhi);
   const u32* dwp = nullptr;
   if (win_part) {
-    u32* hp = (u32*)(ln->h_pin + (size_t)P * 16 + 32);
+    u32* hp = (u32*)(ln->h_pin + (size_t)P * 8 + 64);
     memcpy(hp, win_part, (size_t)P * 4);
     CK(cudaMemcpyAsync(d_wpart, hp, (size_t)P * 4, cudaMemcpyHostToDevice, ln->st));
     dwp = d_wpart;
@@ -576,30 +579,32 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     void* kp = nullptr; void* cp = nullptr;
     CK(arena_alloc(ctx, cap * 8, &kp));
     CK(arena_alloc(ctx, cap * 4, &cp));
-    u64* hm = (u64*)(ln->h_pin + (size_t)P * 16);            // staging for meta = {cursor 0, capacity}
-    hm[0] = 0; hm[1] = cap; hm[2] = 0;
-    CK(cudaMemcpyAsync(d_meta, hm, 24, cudaMemcpyHostToDevice, ln->st));    // meta[2] + flags[2]
-    for (u32 p0 = 0; p0 < P; p0 += gp) {
+    u64* hm = (u64*)(ln->h_pin + (size_t)P * 8);             // staging for meta = {cursor, cursor', capacity, -} + flags
+    hm[0] = 0; hm[1] = 0; hm[2] = cap; hm[3] = 0; hm[4] = 0;
+    CK(cudaMemcpyAsync(d_meta, hm, 40, cudaMemcpyHostToDevice, ln->st));    // meta[4] + flags[2]
+    u32 ngroups = 0;
+    for (u32 p0 = 0; p0 < P; p0 += gp, ngroups++) {
       const u32 g = std::min(gp, P - p0);
       { PROF(KMX_PROF_HASH_HIST);
-        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, S, p0, g, (u32*)ln->sub_counts.p, d_sub_off, d_loff, d_ln,
+        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, p0, g, ngroups, (u32*)ln->sub_counts.p, d_coff, stage, d_loff,
                              d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 0)); }
       { PROF(KMX_PROF_HASH_EMIT);
-        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, S, p0, g, (u32*)ln->sub_counts.p, d_sub_off, d_loff, d_ln,
+        CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, p0, g, ngroups, (u32*)ln->sub_counts.p, d_coff, stage, d_loff,
                              d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 1)); }
     }
-    u64* h_l = (u64*)ln->h_pin;                               // list_off[P] | list_n[P] then meta/flags
-    CK(cudaMemcpyAsync(h_l, d_loff, (size_t)P * 16 + 24, cudaMemcpyDeviceToHost, ln->st));
+    u64* h_l = (u64*)ln->h_pin;                               // list_off[P] then meta[4], flags[2]
+    CK(cudaMemcpyAsync(h_l, d_loff, (size_t)P * 8 + 40, cudaMemcpyDeviceToHost, ln->st));
     CK(cudaStreamSynchronize(ln->st));
-    const u64 D = h_l[2 * P];
-    const u32 ovf = *(u32*)(h_l + 2 * P + 2);
+    const u64 D = h_l[P + (ngroups & 1u)];
+    const u32 ovf = *(u32*)(h_l + P + 4);
     ln->d_est = std::max<u64>(ln->d_est, D + D / 4 + 1024);
     if (ovf) { cap = D + 1024; continue; }                   // the cursor kept counting: exact size now known, histogram is all-zero again
     for (u32 v = 0; v < P; v++) {
       if (win_part && ln->h_cursor[v] == 0) continue;       // unused window
       const u32 smp = win_sample ? win_sample[v] : sample, prt = win_part ? win_part[v] : v;
       ListRef& L = ctx->lists[(size_t)smp * P + prt];
-      L.lo = (u64*)kp + h_l[v]; L.hi = nullptr; L.cnt = (u32*)cp + h_l[v]; L.n = ln->h_cursor[v] ? h_l[P + v] : 0;
+      const u64 end = v + 1 < P ? h_l[v + 1] : D;
+      L.lo = (u64*)kp + h_l[v]; L.hi = nullptr; L.cnt = (u32*)cp + h_l[v]; L.n = end - h_l[v];
     }
     return KMX_OK;
   }

@@ -10,6 +10,8 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 
 
+bool kmx_env_flag(const char* name);       // A/B switches from the environment (s2_hash.cu)
+
 // ---- stage 1 (s1_superk.cu) -------------------------------------------------------------
 struct S1Args {
   const uint8_t* text;          // text base
@@ -49,12 +51,14 @@ struct S2Common {
   u32 max_bcnt;           // host copy of max(bcnt)
 };
 
-// hash mode, histogram path
-static const u32 HIST_SUB = 8192;    // slots per sub-chunk (one CTA of the sweep kernels)
-// hash keys, histogram path: partitions are processed in groups of gp windows that stay L2-resident
-// (phase 0: fill + count survivors per 64K sub-chunk; phase 1: device-side scan/allocation + ordered emit + re-zero)
+// hash keys, histogram path: partitions are processed in groups of gp windows
+// (phase 0: RED fill; phase 1: single-pass ordered sweep = chained scan + emit + re-zero)
+static const u32 HIST_SUB = 8192;    // slots per chunk of the sweep (one CTA, 8 warps x 1024 slots)
+u32 hash_sweep_chunks_per_window(u64 Wbits);
+// staging of the sweep: per 1024-slot slice a run of (slot offset, count) in slot order
+struct SweepStage { uint16_t* idx; u32* cnt; u32* slice_counts; };
 cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi, u32* hist, u32 hard_min,
-                              u32 S, u32 p0, u32 gp, u32* sub_counts, u64* sub_off, u64* list_off, u64* list_n, u64* meta, u32* flags,
+                              u32 p0, u32 gp, u32 group_idx, u32* chunk_counts, u64* chunk_off, SweepStage stage, u64* list_off, u64* meta, u32* flags,
                               u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase);
 cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
 

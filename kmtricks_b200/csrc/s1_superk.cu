@@ -101,88 +101,89 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64(const u32* __restrict__ 
 }
 
 // For newline number g (0-based) at text position pos:
-//   g%4==0 -> sequence of record g/4 starts at pos+1 ; g%4==1 -> it ends at pos (exclusive)
-//   g%4==3 -> next char must be '@' (or end) ; g%4==1 -> next char must be '+'
+//   g%4==0 -> the sequence of record g/4 starts at pos+1 and runs to the next newline
+//   g%4==1 -> next char must be '+' ; g%4==3 -> next char must be '@' (or end)
+// Each thread owns 64 contiguous bytes (blocked, so newline order == thread order) and folds its
+// newline bytes into ONE 64-bit mask, so the per-newline loop runs max-newlines-per-lane times
+// (2-3 for short reads) instead of once per 32-bit word.  The end of a sequence line is found
+// in the CTA's shared mask array (the next set bit after the start), falling back to a byte scan
+// only when the line crosses the 16 KiB tile; length, '\r' strip (kseq drops one trailing '\r'
+// when the line is longer than 1, BankFasta.cpp:476-477) and the maximum length are done here.
 __global__ void __launch_bounds__(FQ_THREADS)
 fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
                const u64* __restrict__ tile_prefix, u32* __restrict__ seq_start,
                u32* __restrict__ seq_len, u64 nrec, u32* __restrict__ flags /* [0]=format error, [1]=max len */)
 {
   __shared__ u32 s_warp[FQ_THREADS / 32];
+  __shared__ u64 s_mask[FQ_THREADS];
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
-  u64 tile0 = (u64)blockIdx.x * FQ_TILE;
-  // each thread owns 64 contiguous bytes here (blocked, so newline order == thread order)
-  u64 off = tile0 + (u64)threadIdx.x * FQ_BYTES_PER_THREAD;
-  u32 wm[16];                                  // per word: 0x80 at every byte that is a newline
-  u32 cnt = 0;
+  const u64 tile0 = (u64)blockIdx.x * FQ_TILE;
+  const u64 off = tile0 + (u64)threadIdx.x * FQ_BYTES_PER_THREAD;
+  u64 mask = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    u64 o = off + j * 16;
+    const u64 o = off + j * 16;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (o < nbytes_total) v = __ldg(base + o / 16);
-    u32 wv[4] = {v.x, v.y, v.z, v.w};
+    const u32 wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      u32 x = wv[q] ^ 0x0A0A0A0Au;
-      u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
-      u32 msk = ~y & 0x80808080u;
-      // drop bytes outside [lead, nbytes_total)
-      u64 wpos = o + 4 * q;
-      if (wpos < lead || wpos + 4 > nbytes_total) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) { u64 pos = wpos + b; if (pos < lead || pos >= nbytes_total) msk &= ~(0x80u << (8 * b)); }
-      }
-      wm[4 * j + q] = msk;
-      cnt += __popc(msk);
+      const u32 x = wv[q] ^ 0x0A0A0A0Au;
+      const u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+      const u32 m = (~y & 0x80808080u) >> 7;                         // bit 8b set <=> byte b is '\n'
+      const u64 nib = ((m * 0x00204081u) >> 21) & 0xFu;              // gather bits 0,8,16,24 -> 0..3
+      mask |= nib << (16 * j + 4 * q);
     }
   }
+  // drop bytes outside [lead, nbytes_total)
+  if (off < lead) { const u64 d = lead - off; mask = d >= 64 ? 0ULL : (mask >> d) << d; }
+  if (off + 64 > nbytes_total) { const u64 keep = nbytes_total > off ? nbytes_total - off : 0; mask = keep == 0 ? 0ULL : (mask & (~0ULL >> (64 - keep))); }
+  const u32 cnt = (u32)__popcll(mask);
   u32 x = cnt;
+#pragma unroll
   for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
   if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  s_mask[threadIdx.x] = mask;
   __syncthreads();
   u32 wbase = 0;
   for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s_warp[i];
   u64 g = tile_prefix[blockIdx.x] + wbase + x - cnt;
-  if (cnt == 0) return;
-#pragma unroll
-  for (int q = 0; q < 16; q++) {
-    u32 msk = wm[q];
-    while (msk) {
-      int bit = __ffs(msk) - 1; msk &= msk - 1;
-      u64 pos = off + 4 * q + (bit >> 3);
-      u64 rec = g >> 2; u32 ph = (u32)(g & 3);
-      u64 tpos = pos - lead;                       // position relative to text start
-      if (rec < nrec) {
-        if (ph == 0) seq_start[rec] = (u32)(tpos + 1);
-        else if (ph == 1) {
-          seq_len[rec] = (u32)tpos;                // end (exclusive); fixed up to a length later
-          if (pos + 1 < nbytes_total && bytes[pos + 1] != '+') atomicOr(&flags[0], 1u);
-        } else if (ph == 3) {
-          if (pos + 1 < nbytes_total && bytes[pos + 1] != '@') atomicOr(&flags[0], 1u);
+  u32 maxlen = 0;
+  u64 msk = mask;
+  while (msk) {
+    const int bit = __ffsll((long long)msk) - 1; msk &= msk - 1;
+    const u64 pos = off + bit;
+    const u64 rec = g >> 2; const u32 ph = (u32)(g & 3);
+    g++;
+    if (rec >= nrec) continue;
+    if (ph == 0) {
+      // end of the sequence line = next newline: own mask, then the following threads' masks
+      u64 end;
+      if (msk) end = off + (__ffsll((long long)msk) - 1);
+      else {
+        u32 t = threadIdx.x + 1;
+        while (t < FQ_THREADS && s_mask[t] == 0) t++;
+        if (t < FQ_THREADS) end = tile0 + (u64)t * FQ_BYTES_PER_THREAD + (__ffsll((long long)s_mask[t]) - 1);
+        else {
+          end = tile0 + FQ_TILE;
+          while (end < nbytes_total && bytes[end] != '\n') end++;
         }
       }
-      g++;
+      const u32 st = (u32)(pos + 1 - lead);
+      u32 len = (u32)(end - (pos + 1));
+      if (len > 1 && bytes[end - 1] == '\r') len--;
+      seq_start[rec] = st; seq_len[rec] = len;
+      maxlen = max(maxlen, len);
+    } else if (ph == 1) {
+      if (pos + 1 < nbytes_total && bytes[pos + 1] != '+') atomicOr(&flags[0], 1u);
+    } else if (ph == 3) {
+      if (pos + 1 < nbytes_total && bytes[pos + 1] != '@') atomicOr(&flags[0], 1u);
     }
   }
-}
-
-// seq_len[r] currently holds the end offset; turn into a length, strip one trailing '\r'
-// (kseq drops it when the line is longer than 1, BankFasta.cpp:476-477), track max length.
-__global__ void fq_fix_len(const uint8_t* __restrict__ text, const u32* __restrict__ seq_start,
-                           u32* __restrict__ seq_len, u64 nrec, u32* __restrict__ flags)
-{
-  u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  u32 len = 0;
-  if (r < nrec) {
-    u32 s = seq_start[r], e = seq_len[r];
-    if (e < s) { atomicOr(&flags[0], 1u); e = s; }
-    len = e - s;
-    if (len > 1 && text[e - 1] == '\r') len--;
-    seq_len[r] = len;
-    if (r == 0 && text[0] != '@') atomicOr(&flags[0], 1u);
-  }
-  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-  if ((threadIdx.x & 31) == 0 && len) atomicMax(&flags[1], len);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bytes[lead] != '@') atomicOr(&flags[0], 1u);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  if ((threadIdx.x & 31) == 0 && maxlen) atomicMax(&flags[1], maxlen);
 }
 
 // ------------------------------------------------------------------------------------
@@ -433,8 +434,7 @@ cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u
     *launches += 2;
   } else {
     fq_index_lines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_prefix, seq_start, seq_len, nrec_cap, flags);
-    fq_fix_len<<<(unsigned)((nrec_cap + 255) / 256), 256, 0, st>>>(text, seq_start, seq_len, nrec_cap, flags);
-    *launches += 2;
+    *launches += 1;
   }
   return cudaGetLastError();
 }

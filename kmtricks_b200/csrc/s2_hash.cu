@@ -15,7 +15,17 @@
 #include "kmx_internal.h"
 #include "records.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace kmx {
+
+// debugging / A-B switches read once from the environment (e.g. KMX_HIST_NOROLL=1)
+bool kmx_env_flag(const char* name)
+{
+  const char* v = getenv(name);
+  return v && *v && *v != '0';
+}
 
 static constexpr int HH_THREADS = 256;
 static constexpr int HH_WARPS = HH_THREADS / 32;
@@ -90,137 +100,268 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
   }
 }
 
-// survivors per 64K-slot sub-chunk: grid = P*S CTAs
-static constexpr int HC_THREADS = 256;
-__global__ void __launch_bounds__(HC_THREADS)
-hash_count_kernel(u64 Wbits, u32 S, const u32* __restrict__ hist, u32 hmin, u32* __restrict__ sub_counts,
-                  const u32* __restrict__ bcnt, u32 p0)
+// ---- rolled variant (k <= 32) ---------------------------------------------------------------
+// The search + 128-bit extraction + bit-reversal of the kernel above cost ~60 of its ~155
+// instructions per k-mer.  Here a CTA stages a tile of HR_TILE records in shared memory and
+// counting-sorts them by their number of k-mers (one shared atomic per record), so that each warp
+// then owns 32 records of (nearly) EQUAL length: lane = record, the forward k-mer and its reverse
+// complement are rolled base by base (~15 instructions), and the warp stays converged because all
+// lanes finish together.  grid = (tiles, windows): blockIdx.x runs fastest, so only a few windows
+// are being filled at any time and they stay L2-resident.
+static constexpr int HR_THREADS = 256;
+static constexpr u32 HR_MAXWIN = 1024;         // windows per launch the persistent kernel can index (power of two)
+
+template <bool D32, bool TAIL64, int HR_TILE>
+__global__ void __launch_bounds__(HR_THREADS)
+hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
+                      int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist, u32 p0, u32 gp, u32* __restrict__ ticket)
 {
-  __shared__ u32 s_warp[HC_THREADS / 32];
-  const u32 wl = blockIdx.x / S, s = blockIdx.x % S, p = p0 + wl;
-  if (bcnt[p] == 0) { if (threadIdx.x == 0) sub_counts[(u64)p * S + s] = 0; return; }   // untouched window
-  const u64 slot0 = (u64)s * HIST_SUB;
-  const u64 slot1 = min(Wbits, slot0 + HIST_SUB);
-  const uint4* __restrict__ h4 = reinterpret_cast<const uint4*>(hist + (u64)wl * Wbits);
-  u32 c = 0;
-  for (u64 q = slot0 / 4 + threadIdx.x; q < slot1 / 4; q += HC_THREADS) {
-    uint4 v = h4[q];
-    c += (v.x >= hmin) + (v.y >= hmin) + (v.z >= hmin) + (v.w >= hmin);
-  }
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __shared__ uint4 s_rec[HR_TILE];
+  __shared__ uint16_t s_perm[HR_TILE];
+  __shared__ u32 s_cnt[64], s_start[64];
+  __shared__ u32 s_pref[HR_MAXWIN + 1];
+  __shared__ u32 s_next;
+  const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  constexpr int HR_PER = HR_TILE / HR_THREADS;
+  const u64 kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+  const int rcsh = 2 * (k - 1);
+  // persistent with in-order tickets: the (window, tile) items are numbered window-major and
+  // handed out by an atomic counter, so the tiles in flight are always consecutive -- all CTAs
+  // work on the same one or two windows (L2-resident REDs) -- and a grid capped at a few CTAs per
+  // SM leaves room on every SM for the issue-bound stage-1 kernel of another lane.
+  for (u32 i = tid; i < HR_MAXWIN; i += HR_THREADS) s_pref[i + 1] = i < gp ? (bcnt[p0 + i] + HR_TILE - 1) / HR_TILE : 0u;
+  if (tid == 0) s_pref[0] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_THREADS / 32; i++) t += s_warp[i]; sub_counts[(u64)p * S + s] = t; }
+  if (w == 0) {                                  // inclusive scan of s_pref[1..HR_MAXWIN] by warp 0
+    u32 carry = 0;
+    for (u32 base = 1; base <= HR_MAXWIN; base += 32) {
+      u32 x = s_pref[base + lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (u32)o) x += y; }
+      s_pref[base + lane] = x + carry;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+  }
+  __syncthreads();
+  const u32 total = s_pref[HR_MAXWIN];
+  u32 nxt = 0;
+  if (tid == 0) { nxt = atomicAdd(ticket, 1u); s_next = nxt; }
+  for (;;) {
+  __syncthreads();                               // previous tile fully consumed, s_next visible
+  const u32 item = s_next;
+  if (item >= total) break;
+  u32 y = 0;                                     // largest y with s_pref[y] <= item
+#pragma unroll
+  for (u32 st = HR_MAXWIN / 2; st > 0; st >>= 1) if (s_pref[y + st] <= item) y += st;
+  const u32 p = p0 + y;
+  const u32 n = bcnt[p];
+  const u64 b0 = boff[p];
+  u32* __restrict__ h = hist + (u64)y * Wbits;
+  const u32 tile0 = (item - s_pref[y]) * HR_TILE;
+  const u32 nt = min((u32)HR_TILE, n - tile0);
+  if (tid < 64) s_cnt[tid] = 0;
+  __syncthreads();
+  if (tid == 0) nxt = atomicAdd(ticket, 1u);     // next ticket: its latency hides behind this tile (stored at the end)
+  u32 nkr[HR_PER], rank[HR_PER];
+#pragma unroll
+  for (int i = 0; i < HR_PER; i++) {
+    const u32 r = tid + HR_THREADS * i;
+    nkr[i] = 0; rank[i] = 0;
+    if (r < nt) {
+      const uint4 v = __ldg(recs + b0 + tile0 + r);
+      s_rec[r] = v;
+      nkr[i] = ((v.w >> 24) - (u32)k + 1u) & 63u;
+      rank[i] = atomicAdd(&s_cnt[nkr[i]], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const u32 c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+    u32 x = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= (u32)o) x += y; }
+    s_start[2 * tid] = x - c0 - c1; s_start[2 * tid + 1] = x - c1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < HR_PER; i++) {
+    const u32 r = tid + HR_THREADS * i;
+    if (r < nt) s_perm[s_start[nkr[i]] + rank[i]] = (uint16_t)r;
+  }
+  __syncthreads();
+  for (u32 g0 = w * 32; g0 < nt; g0 += (HR_THREADS / 32) * 32) {
+    const u32 idx = g0 + lane;
+    u32 nk = 0; u64 f = 0, rc = 0, tlo = 0, thi = 0;
+    if (idx < nt) {
+      const uint4 v = s_rec[s_perm[idx]];
+      const u64 lo = (u64)v.x | ((u64)v.y << 32);
+      const u64 hh = (u64)v.z | ((u64)v.w << 32);
+      const int nb = (int)(hh >> 56);
+      const u64 hi = hh & 0x00FFFFFFFFFFFFFFULL;
+      nk = (u32)(nb - k + 1);
+      f = rec1_kmer(lo, hi, nb, k, 0);
+      rc = revcomp64(f, k);
+      // the nb-k bases after the first k-mer, aligned to the top of (thi:tlo)
+      const int tb = 2 * (nb - k);                     // 0 .. 2*(max_nk-1)
+      if (TAIL64) { thi = tb ? (lo << (64 - tb)) : 0ULL; }
+      else {
+        // 128-bit left shift of (hi:lo) by 128 - tb
+        const int sh = 128 - tb;                       // 128 >= sh > 0
+        if (sh >= 128) { thi = 0; tlo = 0; }
+        else if (sh >= 64) { thi = lo << (sh - 64); tlo = 0; }
+        else { thi = (hi << sh) | (lo >> (64 - sh)); tlo = lo << sh; }
+      }
+    }
+    const u32 maxnk = __reduce_max_sync(0xffffffffu, nk);
+    for (u32 j = 0; j < maxnk; j++) {
+      const u64 c = f < rc ? f : rc;
+      const u64 hv = xxh64_8(c);
+      const u64 key = D32 ? (u64)fastmod64_d32(hv, fm32) : fastmod64(hv, fm);
+      if (j < nk) atomicAdd(h + key, 1u);               // result unused -> RED.ADD
+      const u64 b = thi >> 62;
+      if (TAIL64) thi <<= 2;
+      else { thi = (thi << 2) | (tlo >> 62); tlo <<= 2; }
+      f = ((f << 2) | b) & kmask;
+      rc = (rc >> 2) | ((b ^ 2ULL) << rcsh);
+    }
+  }
+  if (tid == 0) s_next = nxt;
+  }   // items
 }
 
-// One CTA per group: exclusive prefix of the group's sub-chunk survivor counts, output space
-// bump-allocated from a device cursor (no host round trip per group).  meta: [0] cursor (u64),
-// [1] capacity; flags[0] = overflow.  list_off / list_n per partition.
-__global__ void __launch_bounds__(256)
-hash_group_scan_kernel(u32 S, u32 p0, u32 gp, const u32* __restrict__ sub_counts, u64* __restrict__ sub_off,
-                       u64* __restrict__ list_off, u64* __restrict__ list_n, u64* __restrict__ meta, u32* __restrict__ flags)
+// ---- ordered sweep: compact (+re-zero) -> scan -> copy ---------------------------------------
+// The histogram is sparse (a few % of the slots survive hard-min) and every access below is a
+// coalesced stream -- no gathers, no look-back chain:
+//   hash_compact_kernel  streams the windows once (128-bit coalesced loads, DRAM-bound).  Warp w of
+//       a CTA owns a 1024-slot slice of the CTA's chunk; per row of 128 slots the four component
+//       ballots rank the survivors, which are appended IN SLOT ORDER to the slice's own staging
+//       run (slot offset u16 + count u32; capacity = the slice, so it cannot overflow).  Non-zero
+//       words are overwritten with zeros in the same pass, so the histogram is clean again.
+//   hash_scan_kernel     one CTA: exclusive prefix of the chunk counts on top of the running cursor
+//       (bump allocation of the output space, overflow flag, list offsets per window).
+//   hash_copy_kernel     moves every slice's run to its final place as (key u64, count u32).
+static constexpr int HC_THREADS = 256;
+static constexpr int HC_WARPS = HC_THREADS / 32;
+static constexpr u32 HC_SLICE = HIST_SUB / HC_WARPS;                   // 1024 slots per warp slice
+static constexpr int HC_ROWS_PER_WARP = HC_SLICE / 128;                // 8
+static_assert(HC_ROWS_PER_WARP * HC_WARPS * 128 == (int)HIST_SUB, "HIST_SUB must be 8 warps x whole rows");
+
+__global__ void __launch_bounds__(HC_THREADS, 5)
+hash_compact_kernel(u64 Wbits, u32 CW /* chunks per window */, u32* __restrict__ hist, u32 hmin,
+                    uint16_t* __restrict__ st_idx, u32* __restrict__ st_cnt, u32* __restrict__ slice_counts,
+                    u32* __restrict__ chunk_counts, const u32* __restrict__ bcnt, u32 p0)
 {
-  __shared__ u64 s_warp[8];
-  __shared__ u64 s_carry, s_base;
-  const u64 n = (u64)gp * S, first = (u64)p0 * S;
-  // total
-  u64 tot = 0;
-  for (u64 i = threadIdx.x; i < n; i += 256) tot += sub_counts[first + i];
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    u64 t = 0; for (int i = 0; i < 8; i++) t += s_warp[i];
-    const u64 base = atomicAdd((unsigned long long*)&meta[0], (unsigned long long)t);
-    if (base + t > meta[1]) flags[0] = 1u;
-    s_base = base; s_carry = 0;
+  __shared__ u32 s_agg[HC_WARPS];
+  const u32 c = blockIdx.x, wl = c / CW, sub = c - wl * CW;
+  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (bcnt[p0 + wl] == 0) {                           // untouched window: all-zero
+    if (lane == 0) slice_counts[(u64)c * HC_WARPS + w] = 0;
+    if (threadIdx.x == 0) chunk_counts[c] = 0;
+    return;
   }
+  const u32 ltmask = (1u << lane) - 1u;
+  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)wl * Wbits);       // W multiple of 64 -> aligned
+  const u64 qend = Wbits / 4;
+  const u64 q0 = ((u64)sub * HIST_SUB + (u64)w * HC_SLICE) / 4 + lane;
+  uint4 v[HC_ROWS_PER_WARP];
+#pragma unroll
+  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
+    const u64 q = q0 + (u64)j * 32;
+    v[j] = make_uint4(0, 0, 0, 0);
+    if (q < qend) v[j] = __ldcs(h4 + q);
+  }
+  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;  // this slice's staging run
+  u32 run = 0;
+#pragma unroll
+  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
+    const bool sx = v[j].x >= hmin, sy = v[j].y >= hmin, sz = v[j].z >= hmin, sw = v[j].w >= hmin;
+    const u32 bx = __ballot_sync(0xffffffffu, sx), by = __ballot_sync(0xffffffffu, sy);
+    const u32 bz = __ballot_sync(0xffffffffu, sz), bw = __ballot_sync(0xffffffffu, sw);
+    if (bx | by | bz | bw) {
+      u32 o = run + __popc(bx & ltmask) + __popc(by & ltmask) + __popc(bz & ltmask) + __popc(bw & ltmask);
+      const u32 si = (u32)j * 128 + lane * 4;           // slot offset inside the slice
+      if (sx) { st_idx[sbase + o] = (uint16_t)si; st_cnt[sbase + o] = v[j].x; o++; }
+      if (sy) { st_idx[sbase + o] = (uint16_t)(si + 1); st_cnt[sbase + o] = v[j].y; o++; }
+      if (sz) { st_idx[sbase + o] = (uint16_t)(si + 2); st_cnt[sbase + o] = v[j].z; o++; }
+      if (sw) { st_idx[sbase + o] = (uint16_t)(si + 3); st_cnt[sbase + o] = v[j].w; o++; }
+      run += __popc(bx) + __popc(by) + __popc(bz) + __popc(bw);
+    }
+    if (v[j].x | v[j].y | v[j].z | v[j].w) h4[q0 + (u64)j * 32] = make_uint4(0, 0, 0, 0);
+  }
+  if (lane == 0) { s_agg[w] = run; slice_counts[(u64)c * HC_WARPS + w] = run; }
   __syncthreads();
-  for (u64 b = 0; b < n; b += 256) {
-    const u64 i = b + threadIdx.x;
-    const u64 v = i < n ? sub_counts[first + i] : 0;
+  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_WARPS; i++) t += s_agg[i]; chunk_counts[c] = t; }
+}
+
+// One CTA: exclusive prefix of the group's chunk counts on top of the running cursor *base_in.
+__global__ void __launch_bounds__(1024)
+hash_scan_kernel(u32 CW, u32 nchunks, u32 p0, const u32* __restrict__ chunk_counts, u64* __restrict__ chunk_off,
+                 u64* __restrict__ list_off, const u64* __restrict__ base_in, u64* __restrict__ total_out,
+                 const u64* __restrict__ cap_p, u32* __restrict__ flags)
+{
+  __shared__ u64 s_warp[32];
+  __shared__ u64 s_carry;
+  if (threadIdx.x == 0) s_carry = *base_in;
+  __syncthreads();
+  for (u32 b = 0; b < nchunks; b += 1024) {
+    const u32 i = b + threadIdx.x;
+    const u64 v = i < nchunks ? chunk_counts[i] : 0;
     u64 x = v;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
     __syncthreads();
-    u64 wb = 0, all = 0;
-    for (int q = 0; q < 8; q++) { u64 t = s_warp[q]; if (q < (int)(threadIdx.x >> 5)) wb += t; all += t; }
-    const u64 excl = s_base + s_carry + wb + x - v;
-    if (i < n) {
-      sub_off[first + i] = excl;
-      if (i % S == 0) list_off[p0 + i / S] = excl;
+    if (threadIdx.x < 32) {
+      const u64 wv = s_warp[threadIdx.x]; u64 xw = wv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= (u32)o) xw += y; }
+      s_warp[threadIdx.x] = xw - wv;
     }
     __syncthreads();
-    if (threadIdx.x == 0) s_carry += all;
+    const u64 excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
+    if (i < nchunks) {
+      chunk_off[i] = excl;
+      if (i % CW == 0) list_off[p0 + i / CW] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  // list sizes: difference of consecutive partition starts (last one ends at base + total)
-  __syncthreads();
-  for (u32 q = threadIdx.x; q < gp; q += 256) {
-    const u64 st = sub_off[first + (u64)q * S];
-    const u64 en = (q + 1 < gp) ? sub_off[first + (u64)(q + 1) * S] : s_base + s_carry;
-    list_n[p0 + q] = en - st;
+  if (threadIdx.x == 0) {
+    *total_out = s_carry;
+    if (s_carry > *cap_p) flags[0] = 1u;          // output space ran out: nothing is copied, the host retries
   }
 }
 
-// grid = P*S CTAs; CTA (p, s) sweeps slots [s*HIST_SUB, min(W, (s+1)*HIST_SUB)) in order.
-static constexpr int HE_THREADS = 256;
-__global__ void __launch_bounds__(HE_THREADS)
-hash_emit_kernel(u64 Wbits, u32 S, u32* __restrict__ hist, u32 hmin, const u64* __restrict__ sub_off,
-                 const u32* __restrict__ sub_counts, u64* __restrict__ out_keys, u32* __restrict__ out_counts,
-                 const u32* __restrict__ bcnt, const u32* __restrict__ win_part /* NULL: window p holds partition p */,
-                 u32 p0, const u32* __restrict__ flags)
+// grid = chunks: warp w copies slice w's staging run to its final place
+__global__ void __launch_bounds__(HC_THREADS)
+hash_copy_kernel(u64 Wbits, u32 CW, const uint16_t* __restrict__ st_idx, const u32* __restrict__ st_cnt,
+                 const u32* __restrict__ slice_counts, const u32* __restrict__ chunk_counts, const u64* __restrict__ chunk_off,
+                 u64* __restrict__ out_keys, u32* __restrict__ out_counts,
+                 const u32* __restrict__ win_part /* NULL: window p holds partition p */, u32 p0, const u32* __restrict__ flags)
 {
-  __shared__ u32 s_warp[HE_THREADS / 32];
-  __shared__ u32 s_run;
-  const u32 wl = blockIdx.x / S, s = blockIdx.x % S, p = p0 + wl;
-  if (bcnt[p] == 0) return;                               // window never touched: already all-zero
-  const u64 slot0 = (u64)s * HIST_SUB;
-  const u64 slot1 = min(Wbits, slot0 + HIST_SUB);
-  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)wl * Wbits);   // W multiple of 64 -> aligned
-  const u64 key_base = (u64)(win_part ? win_part[p] : p) * Wbits;
-  const u64 obase = sub_off[(u64)p * S + s];
-  if (sub_counts[(u64)p * S + s] == 0 || flags[0]) {     // nothing survives here, or the output space ran out: only re-zero
-    // nothing survives here: still has to clear non-zero (below hard-min) slots
-    for (u64 q = slot0 / 4 + threadIdx.x; q < slot1 / 4; q += HE_THREADS) {
-      uint4 v = h4[q];
-      if (v.x | v.y | v.z | v.w) h4[q] = make_uint4(0, 0, 0, 0);
-    }
-    return;
-  }
-  if (threadIdx.x == 0) s_run = 0;
-  __syncthreads();
-  for (u64 q0 = slot0 / 4; q0 < slot1 / 4; q0 += HE_THREADS) {
-    u64 q = q0 + threadIdx.x;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q < slot1 / 4) {
-      v = h4[q];
-      if (v.x | v.y | v.z | v.w) h4[q] = make_uint4(0, 0, 0, 0);
-    }
-    u32 c = (v.x >= hmin) + (v.y >= hmin) + (v.z >= hmin) + (v.w >= hmin);
-    u32 x = c;
-    for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-    __syncthreads();
-    u32 wb = 0, tot = 0;
-    for (int i = 0; i < HE_THREADS / 32; i++) { u32 t = s_warp[i]; if (i < (int)(threadIdx.x >> 5)) wb += t; tot += t; }
-    u32 run = s_run;
-    u64 o = obase + run + wb + x - c;
-    if (c) {
-      u64 kb = key_base + q * 4;
-      if (v.x >= hmin) { out_keys[o] = kb; out_counts[o] = v.x; o++; }
-      if (v.y >= hmin) { out_keys[o] = kb + 1; out_counts[o] = v.y; o++; }
-      if (v.z >= hmin) { out_keys[o] = kb + 2; out_counts[o] = v.z; o++; }
-      if (v.w >= hmin) { out_keys[o] = kb + 3; out_counts[o] = v.w; o++; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_run = run + tot;
-    __syncthreads();
+  const u32 c = blockIdx.x;
+  if (chunk_counts[c] == 0 || flags[0]) return;
+  const u32 wl = c / CW, sub = c - wl * CW, p = p0 + wl;
+  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  u32 mine = lane < (u32)HC_WARPS ? slice_counts[(u64)c * HC_WARPS + lane] : 0u;
+  const u32 n = __shfl_sync(0xffffffffu, mine, w);
+  u32 wexcl = 0;
+#pragma unroll
+  for (int i = 0; i < HC_WARPS; i++) { const u32 t = __shfl_sync(0xffffffffu, mine, i); if (i < (int)w) wexcl += t; }
+  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;
+  const u64 o = chunk_off[c] + wexcl;
+  const u64 kb = (u64)(win_part ? win_part[p] : p) * Wbits + (u64)sub * HIST_SUB + (u64)w * HC_SLICE;
+  for (u32 i = lane; i < n; i += 32) {
+    out_keys[o + i] = kb + st_idx[sbase + i];
+    out_counts[o + i] = st_cnt[sbase + i];
   }
 }
 
+// phase 0: histogram fill of windows [p0, p0+gp).  phase 1: the ordered sweep of the same windows.
+// meta (device): [0],[1] ping-pong running cursor (group g reads [g&1], writes [(g+1)&1]), [2] capacity.
 cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi, u32* hist, u32 hard_min,
-                              u32 S, u32 p0, u32 gp, u32* sub_counts, u64* sub_off, u64* list_off, u64* list_n, u64* meta, u32* flags,
+                              u32 p0, u32 gp, u32 group_idx, u32* chunk_counts, u64* chunk_off, SweepStage stage, u64* list_off, u64* meta, u32* flags,
                               u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase)
 {
   const u32 hmin = hard_min ? hard_min : 1;
@@ -228,25 +369,48 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
     if (c.max_bcnt) {
       FastMod64 fm; fm.d = mod_d; fm.mlo = mod_mlo; fm.mhi = mod_mhi;
       FastMod32 f32; f32.d = (u32)mod_d; f32.m64 = mod_d >= 2 ? (~0ULL) / mod_d : 0;
-      const bool d32 = mod_d >= 2 && mod_d < (1ULL << 32);
+      const bool d32 = mod_d >= 2 && mod_d < (1ULL << 31);
       unsigned gx = (c.max_bcnt + HH_THREADS - 1) / HH_THREADS;
       if (gx > 592) gx = 592;                 // 4 waves of 148 SMs per partition row at most
       dim3 grid(gx, gp);
       const uint4* recs = (const uint4*)c.records;
-      if (c.W == 1 && d32) hash_hist_kernel<1, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
+      const bool roll = c.W == 1 && gp <= HR_MAXWIN && !kmx_env_flag("KMX_HIST_NOROLL");
+      if (roll) {
+        const bool tail64 = 2 * (KMX_REC1_MAXN - c.k) <= 64;
+        static const int tile = []{ const char* v = getenv("KMX_HR_TILE"); int t = v ? atoi(v) : 256; return (t == 512 || t == 1024) ? t : 256; }();
+        static const int cap = []{ const char* v = getenv("KMX_HIST_CAP"); int t = v ? atoi(v) : 4; return (t >= 1 && t <= 8) ? t : 4; }();
+        const u64 max_items = (u64)((c.max_bcnt + 255) / 256) * gp;
+        const unsigned rgrid = (unsigned)std::min<u64>(max_items, (u64)148 * cap);
+        u32* hist_ticket = flags + 1;
+        cudaError_t me = cudaMemsetAsync(hist_ticket, 0, 4, st);
+        if (me != cudaSuccess) return me;
+#define KMX_ROLL(D, T, TILE) hash_hist_roll_kernel<D, T, TILE><<<rgrid, HR_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0, gp, hist_ticket)
+#define KMX_ROLL_T(TILE) do { if (d32 && tail64) KMX_ROLL(true, true, TILE); else if (d32) KMX_ROLL(true, false, TILE); else if (tail64) KMX_ROLL(false, true, TILE); else KMX_ROLL(false, false, TILE); } while (0)
+        if (tile == 512) KMX_ROLL_T(512); else if (tile == 1024) KMX_ROLL_T(1024); else KMX_ROLL_T(256);
+#undef KMX_ROLL_T
+#undef KMX_ROLL
+      }
+      else if (c.W == 1 && d32) hash_hist_kernel<1, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
       else if (c.W == 1) hash_hist_kernel<1, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
       else if (d32) hash_hist_kernel<2, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
       else hash_hist_kernel<2, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
       *launches += 1;
     }
-    hash_count_kernel<<<gp * S, HC_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_counts, c.bcnt, p0);
-    *launches += 1;
   } else {
-    hash_group_scan_kernel<<<1, 256, 0, st>>>(S, p0, gp, sub_counts, sub_off, list_off, list_n, meta, flags);
-    hash_emit_kernel<<<gp * S, HE_THREADS, 0, st>>>(Wbits, S, hist, hmin, sub_off, sub_counts, out_keys, out_counts, c.bcnt, win_part, p0, flags);
-    *launches += 2;
+    const u32 CW = hash_sweep_chunks_per_window(Wbits);
+    const u64 nchunks64 = (u64)gp * CW;
+    if (nchunks64 >= 0x7FFFFFF0ULL) return cudaErrorInvalidValue;
+    const u32 nchunks = (u32)nchunks64;
+    hash_compact_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, CW, hist, hmin, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, c.bcnt, p0);
+    hash_scan_kernel<<<1, 1024, 0, st>>>(CW, nchunks, p0, chunk_counts, chunk_off, list_off, meta + (group_idx & 1u),
+                                         meta + ((group_idx + 1u) & 1u), meta + 2, flags);
+    hash_copy_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, CW, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, chunk_off,
+                                                     out_keys, out_counts, win_part, p0, flags);
+    *launches += 3;
   }
   return cudaGetLastError();
 }
+
+u32 hash_sweep_chunks_per_window(u64 Wbits) { return (u32)((Wbits + HIST_SUB - 1) / HIST_SUB); }
 
 }  // namespace kmx

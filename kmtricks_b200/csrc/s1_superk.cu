@@ -205,7 +205,7 @@ template <> struct RecT<1> { typedef uint4 type; };
 template <> struct RecT<2> { struct __align__(16) type { uint4 a, b; }; };
 
 static constexpr int S1_THREADS = 128;
-static constexpr int S1_ROUND = 8;
+static_assert(S1_THREADS * 4 == 512, "lds_next_row hard-codes the ring row pitch");
 
 // bits [32*jw, 32*jw+32) of (X >> s), X = big-endian words S(0..nwords) of thread t's packed read
 __device__ __forceinline__ u32 pack_word(const u32* __restrict__ s_pack, u32 t, int nwords, int top_word, int s, int jw)
@@ -219,33 +219,52 @@ __device__ __forceinline__ u32 pack_word(const u32* __restrict__ s_pack, u32 t, 
   return __funnelshift_r(xa, xb, sh);
 }
 
-// suffix-min rebuild of one thread's ring column when a block of wlen m-mers is complete
+// suffix-min rebuild of one thread's ring column when a block of wlen m-mers is complete.
+// The loads of a batch of 8 rows are independent of the running minimum, so they are issued
+// together and only the min/store chain is serial.
 __device__ __noinline__ void ring_suffix_min(u32* __restrict__ col, int wlen)
 {
   u32 accm = 0xFFFFFFFFu;
-  for (int t2 = wlen - 1; t2 >= 0; t2--) {
+  int t2 = wlen - 1;
+  for (; t2 >= 7; t2 -= 8) {
+    u32 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = col[(t2 - q) * S1_THREADS];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { accm = min(accm, v[q]); col[(t2 - q) * S1_THREADS] = accm; }
+  }
+  for (; t2 >= 0; t2--) {
     accm = min(accm, col[t2 * S1_THREADS]);
     col[t2 * S1_THREADS] = accm;
   }
 }
 
-static constexpr u32 S1_EVW = 512;        // cut events per warp queue
-static constexpr u32 S1_EVTHR = 512 - 32 * 9;
+static constexpr u32 S1_EVW = 384;        // cut events per warp queue
+static constexpr u32 S1_EVTHR = S1_EVW - 32 * 9;   // a warp logs <= 32 x 8 (+32 terminators) events between two checks
+
+// shared-memory accesses of the hot loop by 32-bit shared address (keeps the generic->shared window
+// arithmetic out of the per-base instruction stream)
+__device__ __forceinline__ u32 lds_next_row(u32 sa)            // [sa + one ring row (S1_THREADS words)]
+{
+  u32 v; asm volatile("ld.shared.u32 %0, [%1+512];" : "=r"(v) : "r"(sa) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_u32(u32 sa, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2(u32 sa, u32 x, u32 y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sa), "r"(x), "r"(y) : "memory"); }
+// a kernel parameter pinned in a register (the compiler otherwise re-reads it from the constant bank per base)
+__device__ __forceinline__ u32 pin_u32(u32 v) { u32 r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 
 template <int W>
 __global__ void __launch_bounds__(S1_THREADS)
 s1_superk(const S1Args a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: pack[pack_words*128] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | ev[4*512] | evp[4*512] | rank[4*512]
+  // layout: pack[pack_words*128] | ring[wlen*128] | hist[P] | gbase[P] | kc[P] | ev[4*S1_EVW] (uint2: event, partition | rank << 16)
   u32* s_pack = reinterpret_cast<u32*>(smem);
   u32* s_ring = s_pack + a.pack_words * S1_THREADS;
   u32* s_hist = s_ring + a.wlen * S1_THREADS;
   u32* s_gbase = s_hist + a.P;
   u32* s_kc = s_gbase + a.P;
-  u32* s_ev = s_kc + a.P;
-  uint16_t* s_evp = reinterpret_cast<uint16_t*>(s_ev + 4 * S1_EVW);
-  uint16_t* s_rank = s_evp + 4 * S1_EVW;
+  uint2* s_ev = reinterpret_cast<uint2*>(s_kc + a.P + (a.P & 1u));     // 8-byte aligned
   __shared__ u32 s_wcount[4];
   __shared__ u32 s_maxlen;
 
@@ -288,15 +307,18 @@ s1_superk(const S1Args a)
 
   u32 fm = 0, rm = 0;                 // rolling forward / revcomp m-mer
   u32 pk = 0;                         // packed bases of the current 16-base word
-  int bad = k;                        // valid bases still missing before the k-mer ending here is valid
+  u32 vrun = 0;                       // valid bases in a row ending here: the k-mer ending here is valid iff vrun >= k
   u32 nk = 0;                         // k-mers in the open record
   u32 cur_min = 0, cur_p = 0;
   u32 pre = 0xFFFFFFFFu;
-  int j = 0;                          // m-mer index mod wlen (uniform)
+  u32 roff = 0;                       // (m-mer index mod wlen) * 512 = byte offset of the ring row (uniform)
+  const u32 ring_bytes = (u32)wlen * S1_THREADS * 4u;
   u32 wcnt = 0;                       // events in this warp's queue (same value in every lane)
   u32* ring_col = s_ring + tid;
-  u32* evq = s_ev + wid * S1_EVW;
-  uint16_t* evpq = s_evp + wid * S1_EVW;
+  const u32 ring_sa = (u32)__cvta_generic_to_shared(ring_col);
+  u32 ra = ring_sa;                   // shared address of this thread's word in the current ring row
+  const u32 evq_sa = (u32)__cvta_generic_to_shared(s_ev + wid * S1_EVW);
+  const u32 kk = pin_u32((u32)k);
   const uint16_t* __restrict__ repart = a.repart;
   const u32 mm1 = (u32)m - 1u;
 
@@ -316,26 +338,27 @@ s1_superk(const S1Args a)
       fm = ((fm << 2) | c) & mmask;
       rm = (rm >> 2) | ((c ^ 2u) << rsh);
       if (active) pk = (pk << 2) | c;
-      bad = valid ? max(bad - 1, 0) : k;
+      vrun = valid ? vrun + 1u : 0u;
       // lut value of the m-mer ending here (garbage before base m-1: it only feeds windows of
       // k-mers that are not valid yet)
       u32 canon = min(fm, rm);
       u32 t = ~(canon | (canon >> 2));
       t = ((t >> 1) & t) & ban_mask;
       const u32 lutv = (t || i < mm1) ? mmask : canon;
-      const u32 s = (j + 1 < wlen) ? ring_col[(j + 1) * S1_THREADS] : 0xFFFFFFFFu;
-      ring_col[j * S1_THREADS] = lutv;
-      pre = (j == 0) ? lutv : min(pre, lutv);
+      u32 s = 0xFFFFFFFFu;
+      if (roff + 512u < ring_bytes) s = lds_next_row(ra);
+      sts_u32(ra, lutv);
+      pre = (roff == 0) ? lutv : min(pre, lutv);
       const u32 wmin = min(s, pre);
-      if (++j == wlen) { j = 0; ring_suffix_min(ring_col, wlen); }
+      roff += 512u; ra += 512u;
+      if (roff == ring_bytes) { roff = 0; ra = ring_sa; ring_suffix_min(ring_col, wlen); }
       // ---- cut decision (uniform code: ballot-allocated slot in the warp's event queue)
-      const bool kvalid = bad == 0;
+      const bool kvalid = vrun >= kk;
       const bool cut = nk && (!kvalid || wmin != cur_min || nk == max_nk);
       const u32 cmask = __ballot_sync(0xffffffffu, cut);
       if (cut) {
         const u32 slot = wcnt + __popc(cmask & ltmask);
-        evq[slot] = tid | ((i - (u32)k - nk + 1u) << 7) | (nk << 18);    // record = bases [i-(k+nk-1), i)
-        evpq[slot] = (uint16_t)cur_p;
+        sts_v2(evq_sa + slot * 8u, tid | (i << 7) | (nk << 19), cur_p);   // record = bases [i-(k+nk-1), i)
         nk = 0;
       }
       wcnt += __popc(cmask);
@@ -343,13 +366,13 @@ s1_superk(const S1Args a)
       nk += kvalid ? 1u : 0u;
     }
     if ((i0 & 12u) == 12u && i0 + 3 < len) s_pack[(i0 >> 4) * S1_THREADS + tid] = pk;
-    // every 8 bases: publish the partial word, decide (CTA-uniformly) whether to flush the events
+    // every 8 bases: decide (CTA-uniformly) whether to flush the events
     if ((i0 & 4u) || i0 + 4 > maxlen) {
-      const u32 iend = min(i0 + 4u, len);              // bases [0, iend) of this thread are packed
-      if (iend && (iend & 15u)) s_pack[((iend - 1u) >> 4) * S1_THREADS + tid] = pk << (2u * (16u - (iend & 15u)));
       const bool last = i0 + 4 > maxlen;
       const int need = __syncthreads_or((int)(wcnt > S1_EVTHR) | (int)last);
       if (need) {
+        const u32 iend = min(i0 + 4u, len);            // bases [0, iend) of this thread are packed: publish the partial word
+        if (iend && (iend & 15u)) s_pack[((iend - 1u) >> 4) * S1_THREADS + tid] = pk << (2u * (16u - (iend & 15u)));
         if (lane == 0) s_wcount[wid] = wcnt;
         wcnt = 0;
         __syncthreads();
@@ -358,9 +381,9 @@ s1_superk(const S1Args a)
           const u32 n = s_wcount[w];
           for (u32 r = tid; r < n; r += S1_THREADS) {
             const u32 q = w * S1_EVW + r;
-            const u32 p = s_evp[q];
-            s_rank[q] = (uint16_t)atomicAdd(&s_hist[p], 1u);
-            atomicAdd(&s_kc[p], (s_ev[q] >> 18) & 127u);
+            const uint2 e = s_ev[q];
+            s_ev[q].y = e.y | (atomicAdd(&s_hist[e.y], 1u) << 16);
+            atomicAdd(&s_kc[e.y], (e.x >> 19) & 127u);
           }
         }
         __syncthreads();
@@ -379,10 +402,12 @@ s1_superk(const S1Args a)
           const u32 n = s_wcount[w];
           for (u32 r = tid; r < n; r += S1_THREADS) {
             const u32 q = w * S1_EVW + r;
-            const u32 ev = s_ev[q], p = s_evp[q];
-            const u32 t = ev & 127u, st = (ev >> 7) & 2047u, nkr = (ev >> 18) & 127u;
+            const uint2 e = s_ev[q];
+            const u32 ev = e.x, p = e.y & 0xFFFFu;
+            const u32 t = ev & 127u, nkr = (ev >> 19) & 127u;
             const u32 nb = (u32)k + nkr - 1u;                     // bases in the record
-            const u32 pos = s_gbase[p] + s_rank[q];
+            const u32 st = ((ev >> 7) & 4095u) - nb;              // the event carries the base index just past the record
+            const u32 pos = s_gbase[p] + (e.y >> 16);
             const int top = (int)((st + nb - 1u) >> 4);
             const int s = 2 * (int)(15u - ((st + nb - 1u) & 15u));
             const u32 bits = 2u * nb;
@@ -417,7 +442,7 @@ s1_superk(const S1Args a)
 size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P)
 {
   (void)stage_cap;
-  return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + (size_t)4 * S1_EVW * 8;
+  return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + 8 + (size_t)4 * S1_EVW * 8;
 }
 
 cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,

@@ -35,6 +35,14 @@ cudaError_t launch_ht_lookup(u32 P, u32 max_n, const u64* keys, const u32* cnts,
                              const u64* soff, const u32* pcnt, const u64* oo, u64* out_keys, u32* out_cnt, cudaStream_t st, u64* launches);
 cudaError_t launch_ht_union(const MergeList* d_lists, u32 N, u64 max_n, u64* keys, u32* cnts, u64 cap, u32* overflow,
                             u64* out, u32* count, cudaStream_t st, u64* launches);
+cudaError_t launch_ht2_insert_records(const S2Common& c, void* keys, u32* cnts, const u64* toff, const u64* tcap, u32* overflow,
+                                      cudaStream_t st, u64* launches);
+cudaError_t launch_ht2_compact(u32 P, u64 max_cap, const void* keys, const u32* cnts, const u64* toff, const u64* tcap, u32 hard_min,
+                               u64* out_lo, u64* out_hi, u32* pcnt, cudaStream_t st, u64* launches);
+cudaError_t launch_ht2_lookup(u32 P, u32 max_n, const void* keys, const u32* cnts, const u64* toff, const u64* tcap, const u64* slo, const u64* shi,
+                              const u64* soff, const u32* pcnt, const u64* oo, u64* out_lo, u64* out_hi, u32* out_cnt, cudaStream_t st, u64* launches);
+cudaError_t launch_ht2_union(const MergeList* d_lists, u32 N, u64 max_n, void* keys, u64 cap, u32* overflow,
+                             u64* out_lo, u64* out_hi, u32* count, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_solid(const MergeList* d_lists, u32 N, const u32* d_soft, const u64* ulo, const u64* uhi,
                                 u64 nu, int W, u32* solid_in, u64 max_n, cudaStream_t st, u64* launches);
 cudaError_t launch_sparse_emit(const MergeList* d_lists, u32 N, const u32* d_soft, u32 rmin, u32 share, u32 emit_all,
@@ -556,11 +564,11 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
   // device meta: chunk_counts u32[gp*CW] | slice_counts u32[gp*CW*8] ; chunk_off u64[gp*CW] | list_off u64[P] | meta u64[4] |
   // flags u32[2] | win_part u32[P] ; staging: one (u16 slot offset, u32 count) entry per slot of the group (runs per 1024-slot slice)
   const size_t n_chunks = (size_t)gp * hash_sweep_chunks_per_window(Wb);
-  CK(ensure(ln, ln->sub_counts, n_chunks * 4 * 9));
+  CK(ensure(ln, ln->sub_counts, n_chunks * 4 * 9 + ((size_t)gp + 2) * 4));
   CK(ensure(ln, ln->sub_off, n_chunks * 8 + (size_t)P * 8 + 32 + 8 + (size_t)P * 4 + 64));
   CK(ensure(ln, ln->bitmap, n_chunks * HIST_SUB * 6));
   SweepStage stage; stage.cnt = (u32*)ln->bitmap.p; stage.idx = (uint16_t*)(stage.cnt + n_chunks * HIST_SUB);
-  stage.slice_counts = (u32*)ln->sub_counts.p + n_chunks;
+  stage.slice_counts = (u32*)ln->sub_counts.p + n_chunks; stage.done = stage.slice_counts + n_chunks * 8;
   u64* d_coff = (u64*)ln->sub_off.p; u64* d_loff = d_coff + n_chunks; u64* d_meta = d_loff + P;
   u32* d_flags = (u32*)(d_meta + 4); u32* d_wpart = d_flags + 2;
   CK(ensure_pin(ln, (size_t)P * 8 + 64 + (size_t)P * 32 + 256));
@@ -631,7 +639,7 @@ static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
     }
     if (ok == 1) return count_hash_hist(ln, sample, hard_min);
   }
-  if (ctx->prm.key_kind == KMX_KEY_KMER && ctx->W == 1) {
+  if (ctx->prm.key_kind == KMX_KEY_KMER && !kmx_env_flag("KMX_NO_HT")) {
     int rc = count_kmer_ht(ln, sample, hard_min);
     if (rc != KMX_HT_FALLBACK) return rc;
   }

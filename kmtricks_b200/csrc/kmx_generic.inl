@@ -53,11 +53,13 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min)
 
 static u64 next_pow2(u64 v) { u64 p = 1; while (p < v) p <<= 1; return p; }
 
-// k-mer keys, k <= 32: open-addressed hash-count in HBM, then sort only the distinct survivors
+// k-mer keys: open-addressed hash-count in HBM (64-bit slots for k <= 32, 128-bit slots claimed by a
+// 128-bit CAS for k <= 63), then sort only the distinct survivors
 static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
 {
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
+  const int KW = ctx->W;
   double f;
   { std::lock_guard<std::mutex> g(ctx->mu); f = ctx->ht_factor; }
   std::vector<u64> toff(P + 1, 0), tcap(P);
@@ -70,8 +72,9 @@ static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
   if (K == 0) return KMX_OK;
   const u64 TS = toff[P];
   if (TS >= 0xFFFFFFF0ULL) return KMX_HT_FALLBACK;
-  CK(ensure(ln, ln->ht_keys, TS * 8)); CK(ensure(ln, ln->ht_cnts, TS * 4));
+  CK(ensure(ln, ln->ht_keys, TS * 8 * KW)); CK(ensure(ln, ln->ht_cnts, TS * 4));
   CK(ensure(ln, ln->keys_lo, TS * 8)); CK(ensure(ln, ln->keys_lo2, TS * 8));
+  if (KW == 2) { CK(ensure(ln, ln->keys_hi, TS * 8)); CK(ensure(ln, ln->keys_hi2, TS * 8)); }
   // device meta: u64 toff[P] | tcap[P] | oo[P] ; u32 pcnt[P] | overflow
   const size_t mb = (size_t)P * 24 + (size_t)P * 4 + 64;
   CK(ensure(ln, ln->tmp_cnt, mb));
@@ -83,13 +86,18 @@ static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
   CK(cudaMemcpyAsync(d_toff, hp, (size_t)P * 16, cudaMemcpyHostToDevice, ln->st));
   CK(cudaMemsetAsync(d_pcnt, 0, (size_t)P * 4 + 4, ln->st));
   { PROF(KMX_PROF_FILL);
-    CK(cudaMemsetAsync(ln->ht_keys.p, 0xFF, TS * 8, ln->st));
+    CK(cudaMemsetAsync(ln->ht_keys.p, 0xFF, TS * 8 * KW, ln->st));
     CK(cudaMemsetAsync(ln->ht_cnts.p, 0, TS * 4, ln->st)); }
-  S2Common c; c.W = 1; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
+  S2Common c; c.W = KW; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
   c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
-  { PROF(KMX_PROF_EXPAND); CK(launch_ht_insert_records(c, (u64*)ln->ht_keys.p, (u32*)ln->ht_cnts.p, d_toff, d_tcap, d_ovf, ln->st, &ln->launches)); }
-  { PROF(KMX_PROF_RLE); CK(launch_ht_compact(P, max_cap, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap, hard_min,
-                                             (u64*)ln->keys_lo.p, d_pcnt, ln->st, &ln->launches)); }
+  { PROF(KMX_PROF_EXPAND);
+    if (KW == 1) CK(launch_ht_insert_records(c, (u64*)ln->ht_keys.p, (u32*)ln->ht_cnts.p, d_toff, d_tcap, d_ovf, ln->st, &ln->launches));
+    else CK(launch_ht2_insert_records(c, ln->ht_keys.p, (u32*)ln->ht_cnts.p, d_toff, d_tcap, d_ovf, ln->st, &ln->launches)); }
+  { PROF(KMX_PROF_RLE);
+    if (KW == 1) CK(launch_ht_compact(P, max_cap, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap, hard_min,
+                                      (u64*)ln->keys_lo.p, d_pcnt, ln->st, &ln->launches));
+    else CK(launch_ht2_compact(P, max_cap, ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap, hard_min,
+                               (u64*)ln->keys_lo.p, (u64*)ln->keys_hi.p, d_pcnt, ln->st, &ln->launches)); }
   u32* h_pc = (u32*)(ln->h_pin + (size_t)P * 16);
   CK(cudaMemcpyAsync(h_pc, d_pcnt, (size_t)P * 4 + 4, cudaMemcpyDeviceToHost, ln->st));
   CK(cudaStreamSynchronize(ln->st));
@@ -106,20 +114,24 @@ static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
   CK(ensure(ln, ln->sort_work, radix_sort_work_bytes(P, sb.data(), se.data())));
   int in_alt = 0;
   { PROF(KMX_PROF_SORT);
-    CK(segmented_radix_sort(P, sb.data(), se.data(), (u64*)ln->keys_lo.p, nullptr, (u64*)ln->keys_lo2.p, nullptr, 1, 0,
-                            2 * (int)ctx->prm.kmer_size, ln->sort_work.p, &in_alt, ln->st, &ln->launches)); }
-  void *kp = nullptr, *cp = nullptr;
+    CK(segmented_radix_sort(P, sb.data(), se.data(), (u64*)ln->keys_lo.p, KW == 2 ? (u64*)ln->keys_hi.p : nullptr, (u64*)ln->keys_lo2.p,
+                            KW == 2 ? (u64*)ln->keys_hi2.p : nullptr, KW, 0, 2 * (int)ctx->prm.kmer_size, ln->sort_work.p, &in_alt, ln->st, &ln->launches)); }
+  void *kp = nullptr, *khp = nullptr, *cp = nullptr;
   CK(arena_alloc(ctx, D * 8, &kp));
+  if (KW == 2) CK(arena_alloc(ctx, D * 8, &khp));
   CK(arena_alloc(ctx, D * 4, &cp));
   memcpy(hp, oo.data(), P * 8);
   CK(cudaMemcpyAsync(d_oo, hp, (size_t)P * 8, cudaMemcpyHostToDevice, ln->st));
   { PROF(KMX_PROF_RLE);
-    CK(launch_ht_lookup(P, max_n, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap,
-                        (const u64*)(in_alt ? ln->keys_lo2.p : ln->keys_lo.p), d_toff, d_pcnt, d_oo, (u64*)kp, (u32*)cp, ln->st, &ln->launches)); }
+    if (KW == 1) CK(launch_ht_lookup(P, max_n, (const u64*)ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap,
+                                     (const u64*)(in_alt ? ln->keys_lo2.p : ln->keys_lo.p), d_toff, d_pcnt, d_oo, (u64*)kp, (u32*)cp, ln->st, &ln->launches));
+    else CK(launch_ht2_lookup(P, max_n, ln->ht_keys.p, (const u32*)ln->ht_cnts.p, d_toff, d_tcap,
+                              (const u64*)(in_alt ? ln->keys_lo2.p : ln->keys_lo.p), (const u64*)(in_alt ? ln->keys_hi2.p : ln->keys_hi.p),
+                              d_toff, d_pcnt, d_oo, (u64*)kp, (u64*)khp, (u32*)cp, ln->st, &ln->launches)); }
   CK(cudaStreamSynchronize(ln->st));               // pinned staging is reused by the next call
   for (u32 p = 0; p < P; p++) {
     ListRef& L = ctx->lists[(size_t)sample * P + p];
-    L.lo = (u64*)kp + oo[p]; L.hi = nullptr; L.cnt = (u32*)cp + oo[p]; L.n = pcnt[p];
+    L.lo = (u64*)kp + oo[p]; L.hi = khp ? (u64*)khp + oo[p] : nullptr; L.cnt = (u32*)cp + oo[p]; L.n = pcnt[p];
   }
   return KMX_OK;
 }
@@ -142,17 +154,19 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
   //    keys; otherwise (or if the set overflows): concatenate, sort, unique
   u64* ulo = nullptr; u64* uhi = nullptr; u64 nu = 0;
   bool have_union = false;
-  if (KW == 1 && ctx->ht_union_ok) {
+  if (ctx->ht_union_ok) {
     const u64 cap = next_pow2(std::max<u64>(4096, (u64)(2.5 * (double)max_n)));
     if (cap < 0x7FFFFFFFULL) {
-      CK(ensure(ln, ctx->uni_lo2, cap * 8));                         // table
+      CK(ensure(ln, ctx->uni_lo2, cap * 8 * KW));                    // table
       CK(ensure(ln, ctx->uni_lo, cap * 8));                          // distinct keys, unordered
       CK(ensure(ln, ln->keys_lo, cap * 8)); CK(ensure(ln, ln->keys_lo2, cap * 8));
+      if (KW == 2) { CK(ensure(ln, ln->keys_hi, cap * 8)); CK(ensure(ln, ln->keys_hi2, cap * 8)); }
       CK(ensure(ln, ln->tmp_cnt, 64));
       u32* d_cnt = (u32*)ln->tmp_cnt.p; u32* d_ovf = d_cnt + 1;
       CK(cudaMemsetAsync(d_cnt, 0, 8, ln->st));
-      CK(cudaMemsetAsync(ctx->uni_lo2.p, 0xFF, cap * 8, ln->st));
-      CK(launch_ht_union((const MergeList*)ctx->d_lists.p, N, max_n, (u64*)ctx->uni_lo2.p, nullptr, cap, d_ovf, (u64*)ln->keys_lo.p, d_cnt, ln->st, &ln->launches));
+      CK(cudaMemsetAsync(ctx->uni_lo2.p, 0xFF, cap * 8 * KW, ln->st));
+      if (KW == 1) CK(launch_ht_union((const MergeList*)ctx->d_lists.p, N, max_n, (u64*)ctx->uni_lo2.p, nullptr, cap, d_ovf, (u64*)ln->keys_lo.p, d_cnt, ln->st, &ln->launches));
+      else CK(launch_ht2_union((const MergeList*)ctx->d_lists.p, N, max_n, ctx->uni_lo2.p, cap, d_ovf, (u64*)ln->keys_lo.p, (u64*)ln->keys_hi.p, d_cnt, ln->st, &ln->launches));
       u32* hres = (u32*)ln->h_pin;                                   // lists/soft staging was consumed by the H2D copies above
       CK(cudaStreamSynchronize(ln->st));
       CK(cudaMemcpyAsync(hres, d_cnt, 8, cudaMemcpyDeviceToHost, ln->st));
@@ -162,10 +176,12 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
         u64 seg1[2] = {0, nu};
         CK(ensure(ln, ln->sort_work, radix_sort_work_bytes(1, seg1)));
         int alt = 0;
-        CK(segmented_radix_sort(1, seg1, nullptr, (u64*)ln->keys_lo.p, nullptr, (u64*)ln->keys_lo2.p, nullptr, 1, 0,
+        CK(segmented_radix_sort(1, seg1, nullptr, (u64*)ln->keys_lo.p, KW == 2 ? (u64*)ln->keys_hi.p : nullptr, (u64*)ln->keys_lo2.p,
+                                KW == 2 ? (u64*)ln->keys_hi2.p : nullptr, KW, 0,
                                 hash ? bit_length(ctx->prm.window_bits * ctx->prm.nb_partitions - 1) : 2 * (int)ctx->prm.kmer_size,
                                 ln->sort_work.p, &alt, ln->st, &ln->launches));
         ulo = (u64*)(alt ? ln->keys_lo2.p : ln->keys_lo.p);
+        if (KW == 2) uhi = (u64*)(alt ? ln->keys_hi2.p : ln->keys_hi.p);
         have_union = true;
       }
     }

@@ -100,6 +100,66 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
   }
 }
 
+static constexpr int HC_THREADS = 256;
+static constexpr int HC_WARPS = HC_THREADS / 32;
+static constexpr u32 HC_SLICE = HIST_SUB / HC_WARPS;                   // 1024 slots per warp slice
+static constexpr int HC_ROWS_PER_WARP = HC_SLICE / 128;                // 8
+static_assert(HC_ROWS_PER_WARP * HC_WARPS * 128 == (int)HIST_SUB, "HIST_SUB must be 8 warps x whole rows");
+
+struct SweepArgs {
+  u32 CW;                 // chunks per window
+  u32 hmin;
+  uint16_t* st_idx; u32* st_cnt; u32* slice_counts; u32* chunk_counts;
+  u32* done;              // fused kernel only: [gp] tiles finished per window
+};
+
+// chunk c (HIST_SUB slots of window c / CW) by one CTA of HC_THREADS threads; s_agg: HC_WARPS words of shared memory.
+// L2ONLY: the window was just filled by REDs and is expected in L2 (ld.cg); otherwise a streaming read.
+template <bool L2ONLY>
+__device__ __forceinline__ void compact_chunk(u32 c, u64 Wbits, u32* __restrict__ hist, const SweepArgs& sa, bool touched, u32* s_agg)
+{
+  const u32 wl = c / sa.CW, sub = c - wl * sa.CW;
+  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (!touched) {                                     // untouched window: all-zero
+    if (lane == 0) sa.slice_counts[(u64)c * HC_WARPS + w] = 0;
+    if (threadIdx.x == 0) sa.chunk_counts[c] = 0;
+    return;
+  }
+  const u32 hmin = sa.hmin;
+  const u32 ltmask = (1u << lane) - 1u;
+  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)wl * Wbits);       // W multiple of 64 -> aligned
+  const u64 qend = Wbits / 4;
+  const u64 q0 = ((u64)sub * HIST_SUB + (u64)w * HC_SLICE) / 4 + lane;
+  uint4 v[HC_ROWS_PER_WARP];
+#pragma unroll
+  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
+    const u64 q = q0 + (u64)j * 32;
+    v[j] = make_uint4(0, 0, 0, 0);
+    if (q < qend) v[j] = L2ONLY ? __ldcg(h4 + q) : __ldcs(h4 + q);
+  }
+  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;  // this slice's staging run
+  u32 run = 0;
+#pragma unroll
+  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
+    const bool sx = v[j].x >= hmin, sy = v[j].y >= hmin, sz = v[j].z >= hmin, sw = v[j].w >= hmin;
+    const u32 bx = __ballot_sync(0xffffffffu, sx), by = __ballot_sync(0xffffffffu, sy);
+    const u32 bz = __ballot_sync(0xffffffffu, sz), bw = __ballot_sync(0xffffffffu, sw);
+    if (bx | by | bz | bw) {
+      u32 o = run + __popc(bx & ltmask) + __popc(by & ltmask) + __popc(bz & ltmask) + __popc(bw & ltmask);
+      const u32 si = (u32)j * 128 + lane * 4;           // slot offset inside the slice
+      if (sx) { sa.st_idx[sbase + o] = (uint16_t)si; sa.st_cnt[sbase + o] = v[j].x; o++; }
+      if (sy) { sa.st_idx[sbase + o] = (uint16_t)(si + 1); sa.st_cnt[sbase + o] = v[j].y; o++; }
+      if (sz) { sa.st_idx[sbase + o] = (uint16_t)(si + 2); sa.st_cnt[sbase + o] = v[j].z; o++; }
+      if (sw) { sa.st_idx[sbase + o] = (uint16_t)(si + 3); sa.st_cnt[sbase + o] = v[j].w; o++; }
+      run += __popc(bx) + __popc(by) + __popc(bz) + __popc(bw);
+    }
+    if (v[j].x | v[j].y | v[j].z | v[j].w) h4[q0 + (u64)j * 32] = make_uint4(0, 0, 0, 0);
+  }
+  if (lane == 0) { s_agg[w] = run; sa.slice_counts[(u64)c * HC_WARPS + w] = run; }
+  __syncthreads();
+  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_WARPS; i++) t += s_agg[i]; sa.chunk_counts[c] = t; }
+}
+
 // ---- rolled variant (k <= 32) ---------------------------------------------------------------
 // The search + 128-bit extraction + bit-reversal of the kernel above cost ~60 of its ~155
 // instructions per k-mer.  Here a CTA stages a tile of HR_TILE records in shared memory and
@@ -111,11 +171,23 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
 static constexpr int HR_THREADS = 256;
 static constexpr u32 HR_MAXWIN = 1024;         // windows per launch the persistent kernel can index (power of two)
 
-template <bool D32, bool TAIL64, int HR_TILE>
+static constexpr u32 HR_DELAY = 2;             // fused sweep: window z is compacted after the tiles of window z + HR_DELAY were handed out
+
+__device__ __forceinline__ u32 ld_acquire_u32(const u32* p)
+{
+  u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+// FUSED: the item stream interleaves, after the tiles of window b, the compact chunks (compact_chunk)
+// of window b - HR_DELAY, whose fill is complete by then (checked on its done counter): the window is
+// swept while it is still L2-resident and the sweep's instructions hide under the RED-bound fill.
+template <bool D32, bool TAIL64, int HR_TILE, bool FUSED>
 __global__ void __launch_bounds__(HR_THREADS)
 hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
-                      int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist, u32 p0, u32 gp, u32* __restrict__ ticket)
+                      int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist, u32 p0, u32 gp, u32* __restrict__ ticket,
+                      SweepArgs sa)
 {
+  __shared__ u32 s_agg[HC_WARPS];
   __shared__ uint4 s_rec[HR_TILE];
   __shared__ uint16_t s_perm[HR_TILE];
   __shared__ u32 s_cnt[64], s_start[64];
@@ -143,21 +215,44 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
     }
   }
   __syncthreads();
-  const u32 total = s_pref[HR_MAXWIN];
+  const u32 ntile_all = s_pref[HR_MAXWIN];
+  const u32 CWf = FUSED ? sa.CW : 0u;
+  const u32 total = ntile_all + CWf * gp;
+  // item stream: block b in [0, gp + HR_DELAY) = tiles of window b (b < gp), then chunks of window b - HR_DELAY (b >= HR_DELAY)
+  auto bstart = [&](u32 b) -> u32 { return s_pref[min(b, gp)] + CWf * (b > HR_DELAY ? b - HR_DELAY : 0u); };
   u32 nxt = 0;
   if (tid == 0) { nxt = atomicAdd(ticket, 1u); s_next = nxt; }
   for (;;) {
   __syncthreads();                               // previous tile fully consumed, s_next visible
   const u32 item = s_next;
   if (item >= total) break;
-  u32 y = 0;                                     // largest y with s_pref[y] <= item
+  u32 y = 0;                                     // largest block y with bstart(y) <= item
+  if (FUSED) {
+    u32 lo = 0, hi = gp + HR_DELAY;              // bstart(lo) <= item < bstart(hi) = total
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (bstart(mid) <= item) lo = mid; else hi = mid; }
+    y = lo;
+    const u32 off = item - bstart(y);
+    const u32 ty = y < gp ? s_pref[y + 1] - s_pref[y] : 0u;
+    if (off >= ty) {                             // ---- a compact chunk of window z
+      const u32 z = y - HR_DELAY, tz = s_pref[z + 1] - s_pref[z];
+      if (tid == 0) {
+        nxt = atomicAdd(ticket, 1u);
+        while (ld_acquire_u32(sa.done + z) < tz) __nanosleep(64);   // its tiles hold earlier tickets: they are running
+      }
+      __syncthreads();
+      compact_chunk<true>(z * sa.CW + (off - ty), Wbits, hist, sa, tz != 0, s_agg);
+      if (tid == 0) s_next = nxt;
+      continue;
+    }
+  } else {
 #pragma unroll
-  for (u32 st = HR_MAXWIN / 2; st > 0; st >>= 1) if (s_pref[y + st] <= item) y += st;
+    for (u32 st = HR_MAXWIN / 2; st > 0; st >>= 1) if (s_pref[y + st] <= item) y += st;
+  }
   const u32 p = p0 + y;
   const u32 n = bcnt[p];
   const u64 b0 = boff[p];
   u32* __restrict__ h = hist + (u64)y * Wbits;
-  const u32 tile0 = (item - s_pref[y]) * HR_TILE;
+  const u32 tile0 = (item - (FUSED ? bstart(y) : s_pref[y])) * HR_TILE;
   const u32 nt = min((u32)HR_TILE, n - tile0);
   if (tid < 64) s_cnt[tid] = 0;
   __syncthreads();
@@ -225,6 +320,11 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
       rc = (rc >> 2) | ((b ^ 2ULL) << rcsh);
     }
   }
+  if (FUSED) {                                   // this tile's REDs are performed before the window counts it as done
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(sa.done + y, 1u);
+  }
   if (tid == 0) s_next = nxt;
   }   // items
 }
@@ -240,57 +340,12 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
 //   hash_scan_kernel     one CTA: exclusive prefix of the chunk counts on top of the running cursor
 //       (bump allocation of the output space, overflow flag, list offsets per window).
 //   hash_copy_kernel     moves every slice's run to its final place as (key u64, count u32).
-static constexpr int HC_THREADS = 256;
-static constexpr int HC_WARPS = HC_THREADS / 32;
-static constexpr u32 HC_SLICE = HIST_SUB / HC_WARPS;                   // 1024 slots per warp slice
-static constexpr int HC_ROWS_PER_WARP = HC_SLICE / 128;                // 8
-static_assert(HC_ROWS_PER_WARP * HC_WARPS * 128 == (int)HIST_SUB, "HIST_SUB must be 8 warps x whole rows");
-
 __global__ void __launch_bounds__(HC_THREADS, 5)
-hash_compact_kernel(u64 Wbits, u32 CW /* chunks per window */, u32* __restrict__ hist, u32 hmin,
-                    uint16_t* __restrict__ st_idx, u32* __restrict__ st_cnt, u32* __restrict__ slice_counts,
-                    u32* __restrict__ chunk_counts, const u32* __restrict__ bcnt, u32 p0)
+hash_compact_kernel(u64 Wbits, u32* __restrict__ hist, SweepArgs sa, const u32* __restrict__ bcnt, u32 p0)
 {
   __shared__ u32 s_agg[HC_WARPS];
-  const u32 c = blockIdx.x, wl = c / CW, sub = c - wl * CW;
-  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  if (bcnt[p0 + wl] == 0) {                           // untouched window: all-zero
-    if (lane == 0) slice_counts[(u64)c * HC_WARPS + w] = 0;
-    if (threadIdx.x == 0) chunk_counts[c] = 0;
-    return;
-  }
-  const u32 ltmask = (1u << lane) - 1u;
-  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)wl * Wbits);       // W multiple of 64 -> aligned
-  const u64 qend = Wbits / 4;
-  const u64 q0 = ((u64)sub * HIST_SUB + (u64)w * HC_SLICE) / 4 + lane;
-  uint4 v[HC_ROWS_PER_WARP];
-#pragma unroll
-  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
-    const u64 q = q0 + (u64)j * 32;
-    v[j] = make_uint4(0, 0, 0, 0);
-    if (q < qend) v[j] = __ldcs(h4 + q);
-  }
-  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;  // this slice's staging run
-  u32 run = 0;
-#pragma unroll
-  for (int j = 0; j < HC_ROWS_PER_WARP; j++) {
-    const bool sx = v[j].x >= hmin, sy = v[j].y >= hmin, sz = v[j].z >= hmin, sw = v[j].w >= hmin;
-    const u32 bx = __ballot_sync(0xffffffffu, sx), by = __ballot_sync(0xffffffffu, sy);
-    const u32 bz = __ballot_sync(0xffffffffu, sz), bw = __ballot_sync(0xffffffffu, sw);
-    if (bx | by | bz | bw) {
-      u32 o = run + __popc(bx & ltmask) + __popc(by & ltmask) + __popc(bz & ltmask) + __popc(bw & ltmask);
-      const u32 si = (u32)j * 128 + lane * 4;           // slot offset inside the slice
-      if (sx) { st_idx[sbase + o] = (uint16_t)si; st_cnt[sbase + o] = v[j].x; o++; }
-      if (sy) { st_idx[sbase + o] = (uint16_t)(si + 1); st_cnt[sbase + o] = v[j].y; o++; }
-      if (sz) { st_idx[sbase + o] = (uint16_t)(si + 2); st_cnt[sbase + o] = v[j].z; o++; }
-      if (sw) { st_idx[sbase + o] = (uint16_t)(si + 3); st_cnt[sbase + o] = v[j].w; o++; }
-      run += __popc(bx) + __popc(by) + __popc(bz) + __popc(bw);
-    }
-    if (v[j].x | v[j].y | v[j].z | v[j].w) h4[q0 + (u64)j * 32] = make_uint4(0, 0, 0, 0);
-  }
-  if (lane == 0) { s_agg[w] = run; slice_counts[(u64)c * HC_WARPS + w] = run; }
-  __syncthreads();
-  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_WARPS; i++) t += s_agg[i]; chunk_counts[c] = t; }
+  const u32 c = blockIdx.x;
+  compact_chunk<false>(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
 }
 
 // One CTA: exclusive prefix of the group's chunk counts on top of the running cursor *base_in.
@@ -365,6 +420,14 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
                               u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase)
 {
   const u32 hmin = hard_min ? hard_min : 1;
+  const u32 CW = hash_sweep_chunks_per_window(Wbits);
+  // rolled persistent fill for k <= 32; fused with the compact pass unless there is nothing to fill
+  const bool roll = c.W == 1 && gp <= HR_MAXWIN && !kmx_env_flag("KMX_HIST_NOROLL");
+  // (opt-in: measured SLOWER than fill + separate compact -- 1.37 vs 1.02 ms per 1.2e8 k-mers -- because every
+  //  tile needs a __threadfence before its window can be declared filled; kept for experiments)
+  const bool fused = roll && c.max_bcnt != 0 && kmx_env_flag("KMX_HIST_FUSE");
+  SweepArgs sa; sa.CW = CW; sa.hmin = hmin; sa.st_idx = stage.idx; sa.st_cnt = stage.cnt; sa.slice_counts = stage.slice_counts;
+  sa.chunk_counts = chunk_counts; sa.done = stage.done;
   if (phase == 0) {
     if (c.max_bcnt) {
       FastMod64 fm; fm.d = mod_d; fm.mlo = mod_mlo; fm.mhi = mod_mhi;
@@ -374,20 +437,21 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
       if (gx > 592) gx = 592;                 // 4 waves of 148 SMs per partition row at most
       dim3 grid(gx, gp);
       const uint4* recs = (const uint4*)c.records;
-      const bool roll = c.W == 1 && gp <= HR_MAXWIN && !kmx_env_flag("KMX_HIST_NOROLL");
       if (roll) {
         const bool tail64 = 2 * (KMX_REC1_MAXN - c.k) <= 64;
         static const int tile = []{ const char* v = getenv("KMX_HR_TILE"); int t = v ? atoi(v) : 256; return (t == 512 || t == 1024) ? t : 256; }();
         static const int cap = []{ const char* v = getenv("KMX_HIST_CAP"); int t = v ? atoi(v) : 4; return (t >= 1 && t <= 8) ? t : 4; }();
         const u64 max_items = (u64)((c.max_bcnt + 255) / 256) * gp;
         const unsigned rgrid = (unsigned)std::min<u64>(max_items, (u64)148 * cap);
-        u32* hist_ticket = flags + 1;
-        cudaError_t me = cudaMemsetAsync(hist_ticket, 0, 4, st);
+        u32* hist_ticket = stage.done + gp;
+        cudaError_t me = cudaMemsetAsync(stage.done, 0, ((size_t)gp + 1) * 4, st);    // done[gp] | ticket
         if (me != cudaSuccess) return me;
-#define KMX_ROLL(D, T, TILE) hash_hist_roll_kernel<D, T, TILE><<<rgrid, HR_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0, gp, hist_ticket)
-#define KMX_ROLL_T(TILE) do { if (d32 && tail64) KMX_ROLL(true, true, TILE); else if (d32) KMX_ROLL(true, false, TILE); else if (tail64) KMX_ROLL(false, true, TILE); else KMX_ROLL(false, false, TILE); } while (0)
+#define KMX_ROLL(D, T, TILE, F) hash_hist_roll_kernel<D, T, TILE, F><<<rgrid, HR_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0, gp, hist_ticket, sa)
+#define KMX_ROLL_F(D, T, TILE) do { if (fused) KMX_ROLL(D, T, TILE, true); else KMX_ROLL(D, T, TILE, false); } while (0)
+#define KMX_ROLL_T(TILE) do { if (d32 && tail64) KMX_ROLL_F(true, true, TILE); else if (d32) KMX_ROLL_F(true, false, TILE); else if (tail64) KMX_ROLL_F(false, true, TILE); else KMX_ROLL_F(false, false, TILE); } while (0)
         if (tile == 512) KMX_ROLL_T(512); else if (tile == 1024) KMX_ROLL_T(1024); else KMX_ROLL_T(256);
 #undef KMX_ROLL_T
+#undef KMX_ROLL_F
 #undef KMX_ROLL
       }
       else if (c.W == 1 && d32) hash_hist_kernel<1, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
@@ -397,16 +461,15 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
       *launches += 1;
     }
   } else {
-    const u32 CW = hash_sweep_chunks_per_window(Wbits);
     const u64 nchunks64 = (u64)gp * CW;
     if (nchunks64 >= 0x7FFFFFF0ULL) return cudaErrorInvalidValue;
     const u32 nchunks = (u32)nchunks64;
-    hash_compact_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, CW, hist, hmin, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, c.bcnt, p0);
+    if (!fused) { hash_compact_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, hist, sa, c.bcnt, p0); *launches += 1; }
     hash_scan_kernel<<<1, 1024, 0, st>>>(CW, nchunks, p0, chunk_counts, chunk_off, list_off, meta + (group_idx & 1u),
                                          meta + ((group_idx + 1u) & 1u), meta + 2, flags);
     hash_copy_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, CW, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, chunk_off,
                                                      out_keys, out_counts, win_part, p0, flags);
-    *launches += 3;
+    *launches += 2;
   }
   return cudaGetLastError();
 }

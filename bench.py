@@ -416,15 +416,32 @@ def main_kmx(args):
             what = "S3/S4: matrix body written"
         ach = alg / (dur_ms * 1e-3) / 1e9
         traffic = None
-        try:      # dram__bytes_read+write per launch from the committed ncu --set full capture (same launch shape only)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
-            key = {"s1_superk": "s1_superk", "hash_hist": "hash_hist_kernel", "hash_emit": "hash_emit_kernel", "fq_index": "fq_index_lines"}.get(top)
-            if key in tr and args.reads == 1_000_000 and args.read_len == 150 and args.mode == "hash:bf:bin" and args.partitions == 64 and args.bloom_size == 200_000_000:
-                traffic = tr[key]["dram_read_bytes"] + tr[key]["dram_write_bytes"]
+        try:      # dram__bytes_read+write per sample launch of this span's kernels, from the committed ncu --set full capture (same launch shape only)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["spans"]
+            if top in tr and args.reads == 1_000_000 and args.read_len == 150 and args.mode == "hash:bf:bin" and args.partitions == 64 and args.bloom_size == 200_000_000:
+                traffic = tr[top]["dram_read_bytes"] + tr[top]["dram_write_bytes"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": dur_ms, "what": what, "peak_source": peak_src}
+        # whole hot path against the same roofline: SURVEY 8(d) algorithmic bytes of all four stages over the step time
+        try:
+            D = 0
+            nsz = C.c_uint64()
+            for s_ in range(N_tot):
+                for p_ in my_parts:
+                    ck(L.kmx_counts_size(h, s_, p_, C.byref(nsz)), "counts_size")
+                    D += nsz.value
+            key_b = 8 * ((args.kmer_size + 31) // 32) if not args.mode.startswith("hash") else 8
+            alg_s1 = N * (sample_bytes + BUCKET_BYTES_PER_KMER * kmers_step / N)
+            alg_s2 = BUCKET_BYTES_PER_KMER * kmers_step + (key_b + 4) * D / max(world, 1)
+            alg_s34 = (key_b + 4) * D + body_sum[0] * (2 if fmt == "bft" else 1)
+            alg_all = alg_s1 + alg_s2 + alg_s34
+            roof["pipeline"] = {"algorithmic_bytes_per_step": alg_all, "achieved": alg_all / (ms_step * 1e-3) / 1e9,
+                                "frac": alg_all / (ms_step * 1e-3) / 1e9 / peak, "surviving_key_sample_pairs": D,
+                                "what": "S1 text+buckets, S2 buckets+lists, S3/S4 lists+bodies (SURVEY 8d) over ms_per_step"}
+        except Exception as e:      # reporting only
+            roof["pipeline"] = {"error": str(e)}
 
     # ---- end to end through host buffers (pinned FASTQ in, bodies out)
     e2e = None

@@ -239,8 +239,8 @@ __device__ __noinline__ void ring_suffix_min(u32* __restrict__ col, int wlen)
   }
 }
 
-static constexpr u32 S1_EVW = 384;        // cut events per warp queue
-static constexpr u32 S1_EVTHR = S1_EVW - 32 * 9;   // a warp logs <= 32 x 8 (+32 terminators) events between two checks
+static constexpr u32 S1_EVW = 640;        // cut events per warp queue
+static constexpr u32 S1_EVTHR = S1_EVW - 32 * 17;  // a warp logs <= 32 x 16 (+32 terminators) events between two checks
 
 // shared-memory accesses of the hot loop by 32-bit shared address (keeps the generic->shared window
 // arithmetic out of the per-base instruction stream)
@@ -309,7 +309,7 @@ s1_superk(const S1Args a)
   u32 pk = 0;                         // packed bases of the current 16-base word
   u32 vrun = 0;                       // valid bases in a row ending here: the k-mer ending here is valid iff vrun >= k
   u32 nk = 0;                         // k-mers in the open record
-  u32 cur_min = 0, cur_p = 0;
+  u32 cur_min = 0;
   u32 pre = 0xFFFFFFFFu;
   u32 roff = 0;                       // (m-mer index mod wlen) * 512 = byte offset of the ring row (uniform)
   const u32 ring_bytes = (u32)wlen * S1_THREADS * 4u;
@@ -358,16 +358,16 @@ s1_superk(const S1Args a)
       const u32 cmask = __ballot_sync(0xffffffffu, cut);
       if (cut) {
         const u32 slot = wcnt + __popc(cmask & ltmask);
-        sts_v2(evq_sa + slot * 8u, tid | (i << 7) | (nk << 19), cur_p);   // record = bases [i-(k+nk-1), i)
+        sts_v2(evq_sa + slot * 8u, tid | (i << 7) | (nk << 19), cur_min); // record = bases [i-(k+nk-1), i); partition looked up at the flush
         nk = 0;
       }
       wcnt += __popc(cmask);
-      if (kvalid && nk == 0) { cur_min = wmin; cur_p = __ldg(repart + wmin); }
+      if (kvalid && nk == 0) cur_min = wmin;
       nk += kvalid ? 1u : 0u;
     }
     if ((i0 & 12u) == 12u && i0 + 3 < len) s_pack[(i0 >> 4) * S1_THREADS + tid] = pk;
-    // every 8 bases: decide (CTA-uniformly) whether to flush the events
-    if ((i0 & 4u) || i0 + 4 > maxlen) {
+    // every 16 bases: decide (CTA-uniformly) whether to flush the events
+    if ((i0 & 12u) == 12u || i0 + 4 > maxlen) {
       const bool last = i0 + 4 > maxlen;
       const int need = __syncthreads_or((int)(wcnt > S1_EVTHR) | (int)last);
       if (need) {
@@ -382,8 +382,9 @@ s1_superk(const S1Args a)
           for (u32 r = tid; r < n; r += S1_THREADS) {
             const u32 q = w * S1_EVW + r;
             const uint2 e = s_ev[q];
-            s_ev[q].y = e.y | (atomicAdd(&s_hist[e.y], 1u) << 16);
-            atomicAdd(&s_kc[e.y], (e.x >> 19) & 127u);
+            const u32 p = __ldg(repart + e.y);              // e.y = minimizer of the record (Repartitor, PartiInfo.hpp:381)
+            s_ev[q].y = p | (atomicAdd(&s_hist[p], 1u) << 16);
+            atomicAdd(&s_kc[p], (e.x >> 19) & 127u);
           }
         }
         __syncthreads();

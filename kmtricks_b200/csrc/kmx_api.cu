@@ -78,7 +78,7 @@ struct Lane {
   std::string err;
   u64 launches = 0;
   // ---- stage 1
-  DBuf text, seq_start, seq_len, tile_counts, tile_prefix;
+  DBuf text, seq_start, seq_len, tile_counts, tile_prefix, nlmask;
   u64* d_total = nullptr;          // 1 u64
   u32* d_flags = nullptr;          // [0] fmt error [1] max len [2] overflow
   DBuf records;                    // bucket slab
@@ -240,7 +240,7 @@ static void lane_destroy(Lane* ln)
 {
   kmx_ctx* ctx = ln->ctx;
   if (ln->st) cudaStreamSynchronize(ln->st);
-  DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->records, &ln->hist,
+  DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->nlmask, &ln->records, &ln->hist,
                   &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
@@ -449,7 +449,8 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   const u64 ntiles = fq_num_tiles(d_text, nbytes);
   CK(ensure(ln, ln->tile_counts, ntiles * 4));
   CK(ensure(ln, ln->tile_prefix, ntiles * 8));
-  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, ln->d_total, nullptr, nullptr, 0, nullptr, 0, ln->st, &ln->launches)); }
+  CK(ensure(ln, ln->nlmask, ntiles * 256 * 8));             // one bit per text byte, whole 16 KiB tiles
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, (u64*)ln->nlmask.p, ln->d_total, nullptr, nullptr, 0, nullptr, 0, ln->st, &ln->launches)); }
   u64* nl = (u64*)ln->h_pin; uint8_t* last = (uint8_t*)(ln->h_pin + 8);
   CK(cudaMemcpyAsync(nl, ln->d_total, 8, cudaMemcpyDeviceToHost, ln->st));
   CK(cudaMemcpyAsync(last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ln->st));
@@ -461,7 +462,7 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   CK(ensure(ln, ln->seq_start, nrec * 4));
   CK(ensure(ln, ln->seq_len, nrec * 4));
   CK(cudaMemsetAsync(ln->d_flags, 0, 8, ln->st));
-  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, ln->d_total,
+  { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, (u64*)ln->nlmask.p, ln->d_total,
                      (u32*)ln->seq_start.p, (u32*)ln->seq_len.p, nrec, ln->d_flags, 1, ln->st, &ln->launches)); }
   u32* fl = (u32*)ln->h_pin;
   CK(cudaMemcpyAsync(fl, ln->d_flags, 8, cudaMemcpyDeviceToHost, ln->st));

@@ -35,7 +35,7 @@ struct S1Args {
 };
 size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P);
 u64 fq_num_tiles(const uint8_t* text, u64 nbytes);
-cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
+cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix, u64* nlmask /* [tiles * 256] */,
                             u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,
                             int phase, cudaStream_t st, u64* launches);
 cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches);

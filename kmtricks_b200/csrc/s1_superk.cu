@@ -27,18 +27,28 @@ static constexpr int FQ_THREADS = 256;
 static constexpr int FQ_BYTES_PER_THREAD = 64;                 // 4 x uint4
 static constexpr int FQ_TILE = FQ_THREADS * FQ_BYTES_PER_THREAD;
 
-__device__ __forceinline__ u32 count_nl_u32(u32 v)
+// 16-bit mask of the '\n' bytes of one 16-byte piece (bit b = byte b)
+__device__ __forceinline__ u32 nl_mask16(const uint4 v)
 {
-  // bytes equal to 0x0A -> count
-  u32 x = v ^ 0x0A0A0A0Au;                          // zero byte <=> '\n'
-  u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;   // high bit set iff byte != 0 (exact, no borrow)
-  return __popc(~y & 0x80808080u);
+  const u32 wv[4] = {v.x, v.y, v.z, v.w};
+  u32 m16 = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const u32 x = wv[q] ^ 0x0A0A0A0Au;                           // zero byte <=> '\n'
+    const u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;        // high bit set iff byte != 0 (exact, no borrow)
+    const u32 m = (~y & 0x80808080u) >> 7;                       // bit 8b set <=> byte b is '\n'
+    m16 |= (((m * 0x00204081u) >> 21) & 0xFu) << (4 * q);        // gather bits 0,8,16,24 -> 0..3
+  }
+  return m16;
 }
 
-// `base` is the 16B-aligned address at or below the text start, `lead` = text - base.
+// Pass 1 over the text: newline count per 16 KiB tile AND the newline bitmask itself (one u16 per
+// 16-byte piece, bytes outside [lead, nbytes_total) masked off), so that the index pass below reads
+// 1/8 of the bytes and does no SWAR work.  `base` is the 16B-aligned address at or below the text
+// start, `lead` = text - base.
 __global__ void __launch_bounds__(FQ_THREADS)
 fq_count_newlines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total /* lead + n */,
-                  u32* __restrict__ tile_counts)
+                  u32* __restrict__ tile_counts, uint16_t* __restrict__ nlmask)
 {
   __shared__ u32 s_sum[FQ_THREADS / 32];
   u64 tile0 = (u64)blockIdx.x * FQ_TILE;
@@ -46,20 +56,14 @@ fq_count_newlines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total /* 
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     u64 off = tile0 + ((u64)j * FQ_THREADS + threadIdx.x) * 16;
+    u32 m16 = 0;
     if (off < nbytes_total) {
-      uint4 v = __ldg(base + off / 16);
-      u32 wv[4] = {v.x, v.y, v.z, v.w};
-      if (off >= lead && off + 16 <= nbytes_total) {
-        cnt += count_nl_u32(wv[0]) + count_nl_u32(wv[1]) + count_nl_u32(wv[2]) + count_nl_u32(wv[3]);
-      } else {
-#pragma unroll
-        for (int b = 0; b < 16; b++) {
-          u64 pos = off + b;
-          u32 c = (wv[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-          if (pos >= lead && pos < nbytes_total && c == 0x0Au) cnt++;
-        }
-      }
+      m16 = nl_mask16(__ldg(base + off / 16));
+      if (off < lead) { const u32 d = (u32)min((u64)16, lead - off); m16 = d >= 16 ? 0u : (m16 >> d) << d; }
+      if (off + 16 > nbytes_total) m16 &= 0xFFFFu >> (16 - (u32)(nbytes_total - off));
     }
+    nlmask[off / 16] = (uint16_t)m16;                            // the mask array covers whole tiles
+    cnt += __popc(m16);
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = cnt;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64(const u32* __restrict__ 
 // when the line is longer than 1, BankFasta.cpp:476-477) and the maximum length are done here.
 __global__ void __launch_bounds__(FQ_THREADS)
 fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
-               const u64* __restrict__ tile_prefix, u32* __restrict__ seq_start,
+               const u64* __restrict__ tile_prefix, const u64* __restrict__ nlmask64, u32* __restrict__ seq_start,
                u32* __restrict__ seq_len, u64 nrec, u32* __restrict__ flags /* [0]=format error, [1]=max len */)
 {
   __shared__ u32 s_warp[FQ_THREADS / 32];
@@ -119,25 +123,7 @@ fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base);
   const u64 tile0 = (u64)blockIdx.x * FQ_TILE;
   const u64 off = tile0 + (u64)threadIdx.x * FQ_BYTES_PER_THREAD;
-  u64 mask = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const u64 o = off + j * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (o < nbytes_total) v = __ldg(base + o / 16);
-    const u32 wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const u32 x = wv[q] ^ 0x0A0A0A0Au;
-      const u32 y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
-      const u32 m = (~y & 0x80808080u) >> 7;                         // bit 8b set <=> byte b is '\n'
-      const u64 nib = ((m * 0x00204081u) >> 21) & 0xFu;              // gather bits 0,8,16,24 -> 0..3
-      mask |= nib << (16 * j + 4 * q);
-    }
-  }
-  // drop bytes outside [lead, nbytes_total)
-  if (off < lead) { const u64 d = lead - off; mask = d >= 64 ? 0ULL : (mask >> d) << d; }
-  if (off + 64 > nbytes_total) { const u64 keep = nbytes_total > off ? nbytes_total - off : 0; mask = keep == 0 ? 0ULL : (mask & (~0ULL >> (64 - keep))); }
+  const u64 mask = nlmask64[off / 64];                             // written by fq_count_newlines (4 x u16, whole tiles)
   const u32 cnt = (u32)__popcll(mask);
   u32 x = cnt;
 #pragma unroll
@@ -446,7 +432,7 @@ size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P)
   return (size_t)pack_words * S1_THREADS * 4 + (size_t)wlen * S1_THREADS * 4 + (size_t)P * 12 + 8 + (size_t)4 * S1_EVW * 8;
 }
 
-cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix,
+cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u64* tile_prefix, u64* nlmask,
                             u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,
                             int phase, cudaStream_t st, u64* launches)
 {
@@ -455,11 +441,11 @@ cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u
   u64 lead = ta & 15, tot = lead + nbytes;
   u64 ntiles = (tot + FQ_TILE - 1) / FQ_TILE;
   if (phase == 0) {
-    fq_count_newlines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_counts);
+    fq_count_newlines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_counts, (uint16_t*)nlmask);
     scan_u32_to_u64<<<1, 1024, 0, st>>>(tile_counts, tile_prefix, ntiles, d_total);
     *launches += 2;
   } else {
-    fq_index_lines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_prefix, seq_start, seq_len, nrec_cap, flags);
+    fq_index_lines<<<(unsigned)ntiles, FQ_THREADS, 0, st>>>(base, lead, tot, tile_prefix, nlmask, seq_start, seq_len, nrec_cap, flags);
     *launches += 1;
   }
   return cudaGetLastError();

@@ -341,75 +341,78 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
 //       (bump allocation of the output space, overflow flag, list offsets per window).
 //   hash_copy_kernel     moves every slice's run to its final place as (key u64, count u32).
 __global__ void __launch_bounds__(HC_THREADS, 5)
-hash_compact_kernel(u64 Wbits, u32* __restrict__ hist, SweepArgs sa, const u32* __restrict__ bcnt, u32 p0)
+hash_compact_kernel(u64 Wbits, u32 nchunks, u32* __restrict__ hist, SweepArgs sa, const u32* __restrict__ bcnt, u32 p0)
 {
   __shared__ u32 s_agg[HC_WARPS];
-  const u32 c = blockIdx.x;
-  compact_chunk<false>(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
+  for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {       // grid = nchunks, or a persistent grid striding over the chunks
+    compact_chunk<false>(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
+    __syncthreads();
+  }
 }
 
-// One CTA: exclusive prefix of the group's chunk counts on top of the running cursor *base_in.
+// One CTA: exclusive prefix of the group's chunk counts on top of the running cursor *base_in.  Every
+// thread owns a contiguous range: one round of independent loads, one block scan, one round of stores.
 __global__ void __launch_bounds__(1024)
 hash_scan_kernel(u32 CW, u32 nchunks, u32 p0, const u32* __restrict__ chunk_counts, u64* __restrict__ chunk_off,
                  u64* __restrict__ list_off, const u64* __restrict__ base_in, u64* __restrict__ total_out,
                  const u64* __restrict__ cap_p, u32* __restrict__ flags)
 {
   __shared__ u64 s_warp[32];
-  __shared__ u64 s_carry;
-  if (threadIdx.x == 0) s_carry = *base_in;
+  const u32 per = (nchunks + 1023u) / 1024u;
+  const u32 i0 = min(nchunks, threadIdx.x * per), i1 = min(nchunks, i0 + per);
+  u64 sum = 0;
+  for (u32 i = i0; i < i1; i++) sum += chunk_counts[i];
+  u64 x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
   __syncthreads();
-  for (u32 b = 0; b < nchunks; b += 1024) {
-    const u32 i = b + threadIdx.x;
-    const u64 v = i < nchunks ? chunk_counts[i] : 0;
-    u64 x = v;
+  if (threadIdx.x < 32) {
+    const u64 wv = s_warp[threadIdx.x]; u64 xw = wv;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const u64 wv = s_warp[threadIdx.x]; u64 xw = wv;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= (u32)o) xw += y; }
-      s_warp[threadIdx.x] = xw - wv;
-    }
-    __syncthreads();
-    const u64 excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
-    if (i < nchunks) {
-      chunk_off[i] = excl;
-      if (i % CW == 0) list_off[p0 + i / CW] = excl;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = excl + v;
-    __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= (u32)o) xw += y; }
+    s_warp[threadIdx.x] = xw - wv;
   }
-  if (threadIdx.x == 0) {
-    *total_out = s_carry;
-    if (s_carry > *cap_p) flags[0] = 1u;          // output space ran out: nothing is copied, the host retries
+  __syncthreads();
+  u64 run = *base_in + s_warp[threadIdx.x >> 5] + x - sum;
+  for (u32 i = i0; i < i1; i++) {
+    chunk_off[i] = run;
+    if (i % CW == 0) list_off[p0 + i / CW] = run;
+    run += chunk_counts[i];
+  }
+  if (threadIdx.x == 1023) {                      // its range ends at nchunks: run is the grand total
+    *total_out = run;
+    if (run > *cap_p) flags[0] = 1u;              // output space ran out: nothing is copied, the host retries
   }
 }
 
-// grid = chunks: warp w copies slice w's staging run to its final place
+// one warp per chunk: copies the chunk's 8 staging runs to their final place as (key u64, count u32)
 __global__ void __launch_bounds__(HC_THREADS)
-hash_copy_kernel(u64 Wbits, u32 CW, const uint16_t* __restrict__ st_idx, const u32* __restrict__ st_cnt,
+hash_copy_kernel(u64 Wbits, u32 CW, u32 nchunks, const uint16_t* __restrict__ st_idx, const u32* __restrict__ st_cnt,
                  const u32* __restrict__ slice_counts, const u32* __restrict__ chunk_counts, const u64* __restrict__ chunk_off,
                  u64* __restrict__ out_keys, u32* __restrict__ out_counts,
                  const u32* __restrict__ win_part /* NULL: window p holds partition p */, u32 p0, const u32* __restrict__ flags)
 {
-  const u32 c = blockIdx.x;
-  if (chunk_counts[c] == 0 || flags[0]) return;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 c = blockIdx.x * HC_WARPS + (threadIdx.x >> 5);
+  if (c >= nchunks || flags[0]) return;
+  const u32 mine = lane < (u32)HC_WARPS ? slice_counts[(u64)c * HC_WARPS + lane] : 0u;
+  if (__ballot_sync(0xffffffffu, mine != 0) == 0) return;
   const u32 wl = c / CW, sub = c - wl * CW, p = p0 + wl;
-  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  u32 mine = lane < (u32)HC_WARPS ? slice_counts[(u64)c * HC_WARPS + lane] : 0u;
-  const u32 n = __shfl_sync(0xffffffffu, mine, w);
-  u32 wexcl = 0;
+  u32 x = mine;                                    // inclusive scan over the 8 slices
 #pragma unroll
-  for (int i = 0; i < HC_WARPS; i++) { const u32 t = __shfl_sync(0xffffffffu, mine, i); if (i < (int)w) wexcl += t; }
-  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;
-  const u64 o = chunk_off[c] + wexcl;
-  const u64 kb = (u64)(win_part ? win_part[p] : p) * Wbits + (u64)sub * HIST_SUB + (u64)w * HC_SLICE;
-  for (u32 i = lane; i < n; i += 32) {
-    out_keys[o + i] = kb + st_idx[sbase + i];
-    out_counts[o + i] = st_cnt[sbase + i];
+  for (int o = 1; o < HC_WARPS; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (u32)o) x += y; }
+  const u64 obase = chunk_off[c];
+  const u64 kb = (u64)(win_part ? win_part[p] : p) * Wbits + (u64)sub * HIST_SUB;
+#pragma unroll
+  for (int w = 0; w < HC_WARPS; w++) {
+    const u32 n = __shfl_sync(0xffffffffu, mine, w);
+    const u64 o = obase + __shfl_sync(0xffffffffu, x - mine, w);
+    const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;
+    for (u32 i = lane; i < n; i += 32) {
+      out_keys[o + i] = kb + (u64)w * HC_SLICE + st_idx[sbase + i];
+      out_counts[o + i] = st_cnt[sbase + i];
+    }
   }
 }
 
@@ -464,10 +467,15 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
     const u64 nchunks64 = (u64)gp * CW;
     if (nchunks64 >= 0x7FFFFFF0ULL) return cudaErrorInvalidValue;
     const u32 nchunks = (u32)nchunks64;
-    if (!fused) { hash_compact_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, hist, sa, c.bcnt, p0); *launches += 1; }
+    if (!fused) {
+      static const unsigned ccap = []{ const char* v = getenv("KMX_COMPACT_CAP"); int t = v ? atoi(v) : 0; return (unsigned)((t >= 0 && t <= 8) ? t : 0); }();
+      const unsigned cgrid = ccap ? std::min<unsigned>(nchunks, 148u * ccap) : nchunks;
+      hash_compact_kernel<<<cgrid, HC_THREADS, 0, st>>>(Wbits, nchunks, hist, sa, c.bcnt, p0);
+      *launches += 1;
+    }
     hash_scan_kernel<<<1, 1024, 0, st>>>(CW, nchunks, p0, chunk_counts, chunk_off, list_off, meta + (group_idx & 1u),
                                          meta + ((group_idx + 1u) & 1u), meta + 2, flags);
-    hash_copy_kernel<<<nchunks, HC_THREADS, 0, st>>>(Wbits, CW, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, chunk_off,
+    hash_copy_kernel<<<(nchunks + HC_WARPS - 1) / HC_WARPS, HC_THREADS, 0, st>>>(Wbits, CW, nchunks, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, chunk_off,
                                                      out_keys, out_counts, win_part, p0, flags);
     *launches += 2;
   }

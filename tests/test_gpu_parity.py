@@ -82,3 +82,30 @@ def test_many_samples_many_partitions(name, case, N):
     samples = [[synth.make_fastq(3, s, 120, L=150, G=6000, d=1e-2, e=5e-3, revcomp=True)] for s in range(N)]
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], N)
+
+
+@pytest.mark.parametrize("flag,name", [
+    ("KMX_HIST_NOROLL", "hash_bf"),        # k <= 32 histogram fill by the search-and-extract kernel (the k > 32 / fallback kernel)
+    ("KMX_HIST_FUSE", "hash_bf"),          # opt-in fused fill + compact persistent kernel (done counters, fences)
+    ("KMX_HIST_FUSE", "hash_count"),
+    ("KMX_NO_HT", "kmer_count"),           # generic path: expand -> segmented radix sort -> run-length (fallback of the hash-count)
+    ("KMX_NO_HT", "k63_kmer_pa"),
+])
+def test_fallback_paths_stay_exact(flag, name, synth_samples, monkeypatch):
+    """The alternative stage-2 paths behind the environment switches give the same bytes as the default ones."""
+    monkeypatch.setenv(flag, "1")
+    got, want = _run_both(synth_samples, CASES[name])
+    _compare(got, want, CASES[name]["P"], len(synth_samples))
+
+
+def test_hash_mode_larger_sample_all_paths(monkeypatch):
+    """One sample large enough that every partition spans several histogram tiles and sweep chunks
+    (tile tickets wrap over windows, partial last chunk), default and fused kernels."""
+    from kmtricks_b200 import synth
+    samples = [[synth.make_fastq(7, s, 30000, L=150, G=200000, d=3e-3, e=3e-3, revcomp=True)] for s in range(2)]
+    case = dict(k=31, P=6, mode="hash:bf:bin", hard_min=2, bloom_size=3_000_000)
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    monkeypatch.setenv("KMX_HIST_FUSE", "1")
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))

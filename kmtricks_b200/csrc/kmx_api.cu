@@ -105,6 +105,7 @@ struct kmx_ctx {
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
+  bool hist16 = true;              // hash histogram with 16-bit counters until one wraps (count_hash_hist)
   int active_lanes = 1;            // lanes running concurrently (sizes the L2-resident histogram groups)
   double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
   bool ht_union_ok = true;
@@ -557,24 +558,33 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     const u64 budget = ((u64)100 << 20) / (u64)std::max(1, ctx->active_lanes);
     gp = (u32)std::max<u64>(1, std::min<u64>(P, budget / (Wb * 4)));
   }
-  const size_t hist_bytes = (size_t)gp * Wb * 4;
-  if (ln->hist.cap < hist_bytes) {
-    CK(ensure(ln, ln->hist, hist_bytes));
-    CK(cudaMemsetAsync(ln->hist.p, 0, ln->hist.cap, ln->st));
-  }
+  // 16-bit counters (half the histogram bytes) until a sample makes one wrap; from then on 32-bit counters
+  bool h16;
+  { std::lock_guard<std::mutex> g(ctx->mu); h16 = ctx->hist16 && !kmx_env_flag("KMX_HIST32"); }
+  auto ensure_hist = [&](bool half) -> int {
+    const size_t hist_bytes = (size_t)gp * Wb * (half ? 2 : 4);
+    if (ln->hist.cap < hist_bytes) {
+      CK(ensure(ln, ln->hist, hist_bytes));
+      CK(cudaMemsetAsync(ln->hist.p, 0, ln->hist.cap, ln->st));
+    }
+    return KMX_OK;
+  };
+  { int rc = ensure_hist(h16); if (rc) return rc; }
   // device meta: chunk_counts u32[gp*CW] | slice_counts u32[gp*CW*8] ; chunk_off u64[gp*CW] | list_off u64[P] | meta u64[4] |
   // flags u32[2] | win_part u32[P] ; staging: one (u16 slot offset, u32 count) entry per slot of the group (runs per 1024-slot slice)
   const size_t n_chunks = (size_t)gp * hash_sweep_chunks_per_window(Wb);
-  CK(ensure(ln, ln->sub_counts, n_chunks * 4 * 9 + ((size_t)gp + 2) * 4));
+  const size_t sc_words = (n_chunks * 9 + (size_t)gp + 2 + 1) & ~(size_t)1;      // u32 words before the (8-byte aligned) window sums
+  CK(ensure(ln, ln->sub_counts, sc_words * 4 + (size_t)gp * 8));
   CK(ensure(ln, ln->sub_off, n_chunks * 8 + (size_t)P * 8 + 32 + 8 + (size_t)P * 4 + 64));
   CK(ensure(ln, ln->bitmap, n_chunks * HIST_SUB * 6));
   SweepStage stage; stage.cnt = (u32*)ln->bitmap.p; stage.idx = (uint16_t*)(stage.cnt + n_chunks * HIST_SUB);
   stage.slice_counts = (u32*)ln->sub_counts.p + n_chunks; stage.done = stage.slice_counts + n_chunks * 8;
+  stage.win_sum = (u64*)((u32*)ln->sub_counts.p + sc_words);
   u64* d_coff = (u64*)ln->sub_off.p; u64* d_loff = d_coff + n_chunks; u64* d_meta = d_loff + P;
   u32* d_flags = (u32*)(d_meta + 4); u32* d_wpart = d_flags + 2;
   CK(ensure_pin(ln, (size_t)P * 8 + 64 + (size_t)P * 32 + 256));
   S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
-  c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
+  c.bcnt = ln->d_cursor; c.kcnt = ln->d_kcnt; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   u64 mlo, mhi; fastmod_magic(Wb, mlo, mhi);
   const u32* dwp = nullptr;
   if (win_part) {
@@ -584,7 +594,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     dwp = d_wpart;
   }
   u64 cap = std::max<u64>(4096, ln->d_est);
-  for (int attempt = 0; attempt < 2; attempt++) {
+  for (int attempt = 0; attempt < 4; attempt++) {
     void* kp = nullptr; void* cp = nullptr;
     CK(arena_alloc(ctx, cap * 8, &kp));
     CK(arena_alloc(ctx, cap * 4, &cp));
@@ -596,16 +606,23 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
       const u32 g = std::min(gp, P - p0);
       { PROF(KMX_PROF_HASH_HIST);
         CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, p0, g, ngroups, (u32*)ln->sub_counts.p, d_coff, stage, d_loff,
-                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 0)); }
+                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 0, h16)); }
       { PROF(KMX_PROF_HASH_EMIT);
         CK(launch_hash_group(c, Wb, Wb, mlo, mhi, (u32*)ln->hist.p, hard_min, p0, g, ngroups, (u32*)ln->sub_counts.p, d_coff, stage, d_loff,
-                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 1)); }
+                             d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 1, h16)); }
     }
     u64* h_l = (u64*)ln->h_pin;                               // list_off[P] then meta[4], flags[2]
     CK(cudaMemcpyAsync(h_l, d_loff, (size_t)P * 8 + 40, cudaMemcpyDeviceToHost, ln->st));
     CK(cudaStreamSynchronize(ln->st));
     const u64 D = h_l[P + (ngroups & 1u)];
-    const u32 ovf = *(u32*)(h_l + P + 4);
+    const u32 ovf = *(u32*)(h_l + P + 4), wrapped = *((u32*)(h_l + P + 4) + 1);
+    if (h16 && wrapped) {                                     // a 16-bit counter wrapped: the lists are void, the histogram is all-zero again
+      { std::lock_guard<std::mutex> g(ctx->mu); ctx->hist16 = false; }
+      h16 = false;
+      int rc = ensure_hist(false);
+      if (rc) return rc;
+      continue;
+    }
     ln->d_est = std::max<u64>(ln->d_est, D + D / 4 + 1024);
     if (ovf) { cap = D + 1024; continue; }                   // the cursor kept counting: exact size now known, histogram is all-zero again
     for (u32 v = 0; v < P; v++) {
@@ -617,7 +634,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     }
     return KMX_OK;
   }
-  return fail(ln, KMX_ERR_CUDA, "hash-count output space overflowed twice");
+  return fail(ln, KMX_ERR_CUDA, "hash-count output space overflowed repeatedly");
 }
 
 static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)

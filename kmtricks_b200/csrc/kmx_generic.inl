@@ -20,7 +20,7 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min)
   u64* d_koff = (u64*)ln->tmp_cnt.p; u32* d_kcur = (u32*)(d_koff + P + 1);
   CK(cudaMemcpyAsync(d_koff, koff.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ln->st));
   CK(cudaMemsetAsync(d_kcur, 0, P * 4, ln->st));
-  S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
+  S2Common c; c.W = ctx->W; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff; c.kcnt = ln->d_kcnt;
   c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   u64 mlo = 0, mhi = 0; const u64 Wb = ctx->prm.window_bits;
   if (hash) fastmod_magic(Wb, mlo, mhi);
@@ -88,7 +88,7 @@ static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
   { PROF(KMX_PROF_FILL);
     CK(cudaMemsetAsync(ln->ht_keys.p, 0xFF, TS * 8 * KW, ln->st));
     CK(cudaMemsetAsync(ln->ht_cnts.p, 0, TS * 4, ln->st)); }
-  S2Common c; c.W = KW; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff;
+  S2Common c; c.W = KW; c.k = (int)ctx->prm.kmer_size; c.P = P; c.records = ln->records.p; c.boff = ln->d_boff; c.kcnt = ln->d_kcnt;
   c.bcnt = ln->d_cursor; c.max_bcnt = *std::max_element(ln->h_cursor.begin(), ln->h_cursor.end());
   { PROF(KMX_PROF_EXPAND);
     if (KW == 1) CK(launch_ht_insert_records(c, (u64*)ln->ht_keys.p, (u32*)ln->ht_cnts.p, d_toff, d_tcap, d_ovf, ln->st, &ln->launches));

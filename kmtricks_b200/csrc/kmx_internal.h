@@ -48,6 +48,7 @@ struct S2Common {
   const void* records;    // bucket slab
   const u64* boff;        // [P] device
   const u32* bcnt;        // [P] device: records per partition
+  const u64* kcnt;        // [P] device: k-mers per partition (hash path, 16-bit counters: overflow check)
   u32 max_bcnt;           // host copy of max(bcnt)
 };
 
@@ -56,10 +57,10 @@ struct S2Common {
 static const u32 HIST_SUB = 8192;    // slots per chunk of the sweep (one CTA, 8 warps x 1024 slots)
 u32 hash_sweep_chunks_per_window(u64 Wbits);
 // staging of the sweep: per 1024-slot slice a run of (slot offset, count) in slot order
-struct SweepStage { uint16_t* idx; u32* cnt; u32* slice_counts; u32* done /* [gp] tiles done per window | ticket */; };
+struct SweepStage { uint16_t* idx; u32* cnt; u32* slice_counts; u32* done /* [gp] tiles done per window | ticket */; u64* win_sum /* [gp] */; };
 cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi, u32* hist, u32 hard_min,
                               u32 p0, u32 gp, u32 group_idx, u32* chunk_counts, u64* chunk_off, SweepStage stage, u64* list_off, u64* meta, u32* flags,
-                              u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase);
+                              u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase, bool h16);
 cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
 
 // generic path: expand -> keys, segmented radix sort, run-length

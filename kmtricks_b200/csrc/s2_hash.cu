@@ -37,7 +37,18 @@ static constexpr int HH_WARPS = HH_THREADS / 32;
 // variant with per-lane contiguous chunks was measured 1.9x SLOWER: lanes cross record
 // boundaries at different steps, so the warp pays extract + roll at every step).
 // The histogram update is a fire-and-forget RED; the modulo is an exact 32-bit Barrett when W < 2^32.
-template <int W, bool D32>
+// Counter width.  H16: two 16-bit counters per 32-bit word (slot s = half s&1 of word s>>1), incremented by a RED of
+// 1 << 16*(s&1).  A counter that reaches 65536 wraps (and, from the low half, carries into its neighbour): the sweep
+// detects ANY such event exactly, because it makes the sum of all fields of the window fall short of the number of
+// k-mers inserted (known from stage 1); the sample is then redone with 32-bit counters.  Half the histogram bytes.
+template <bool H16>
+__device__ __forceinline__ void hist_inc(u32* __restrict__ h, u64 key)
+{
+  if (H16) atomicAdd(h + (key >> 1), 1u << (16u * (u32)(key & 1ULL)));   // result unused -> RED.ADD
+  else atomicAdd(h + key, 1u);
+}
+
+template <int W, bool D32, bool H16>
 __global__ void __launch_bounds__(HH_THREADS)
 hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
                  int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist, u32 p0)
@@ -48,7 +59,7 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
   const u32 n = bcnt[p];
   const u64 b0 = boff[p];
   const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  u32* __restrict__ h = hist + (u64)blockIdx.y * Wbits;
+  u32* __restrict__ h = hist + (u64)blockIdx.y * (Wbits >> (H16 ? 1 : 0));
   for (u32 r0 = (blockIdx.x * HH_WARPS + w) * 32; r0 < n; r0 += gridDim.x * HH_THREADS) {
     const u32 r = r0 + lane;
     u32 nk = 0;
@@ -94,7 +105,7 @@ hash_hist_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, c
         u64 clo, chi; canon2(rec, k, j, clo, chi);
         { const u64 hv = xxh64_16(clo, chi); key = D32 ? (u64)fastmod64_d32(hv, fm32) : fastmod64(hv, fm); }
       }
-      atomicAdd(h + key, 1u);       // result unused -> RED.ADD
+      hist_inc<H16>(h, key);
     }
     __syncwarp();
   }
@@ -111,6 +122,7 @@ struct SweepArgs {
   u32 hmin;
   uint16_t* st_idx; u32* st_cnt; u32* slice_counts; u32* chunk_counts;
   u32* done;              // fused kernel only: [gp] tiles finished per window
+  u64* win_sum;           // 16-bit counters only: [gp] sum of all fields of the window (overflow check)
 };
 
 // chunk c (HIST_SUB slots of window c / CW) by one CTA of HC_THREADS threads; s_agg: HC_WARPS words of shared memory.
@@ -160,6 +172,65 @@ __device__ __forceinline__ void compact_chunk(u32 c, u64 Wbits, u32* __restrict_
   if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_WARPS; i++) t += s_agg[i]; sa.chunk_counts[c] = t; }
 }
 
+// 16-bit counters: a uint4 holds 8 slots, a row of 32 lanes 256 slots, a 1024-slot slice 4 rows.  Besides compacting,
+// every warp adds the sum of all its fields to win_sum[window] (the overflow check, see hist_inc).
+static constexpr int HC16_ROWS_PER_WARP = HC_SLICE / 256;              // 4
+__device__ __forceinline__ void compact_chunk16(u32 c, u64 Wbits, u32* __restrict__ hist, const SweepArgs& sa, bool touched, u32* s_agg)
+{
+  const u32 wl = c / sa.CW, sub = c - wl * sa.CW;
+  const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (!touched) {                                     // untouched window: all-zero
+    if (lane == 0) sa.slice_counts[(u64)c * HC_WARPS + w] = 0;
+    if (threadIdx.x == 0) sa.chunk_counts[c] = 0;
+    return;
+  }
+  const u32 hmin = sa.hmin;
+  const u32 ltmask = (1u << lane) - 1u;
+  uint4* __restrict__ h4 = reinterpret_cast<uint4*>(hist + (u64)wl * (Wbits >> 1));   // W multiple of 64 -> 128-byte aligned
+  const u64 qend = Wbits / 8;
+  const u64 q0 = ((u64)sub * HIST_SUB + (u64)w * HC_SLICE) / 8 + lane;
+  uint4 v[HC16_ROWS_PER_WARP];
+#pragma unroll
+  for (int j = 0; j < HC16_ROWS_PER_WARP; j++) {
+    const u64 q = q0 + (u64)j * 32;
+    v[j] = make_uint4(0, 0, 0, 0);
+    if (q < qend) v[j] = __ldcs(h4 + q);
+  }
+  const u64 sbase = ((u64)c * HC_WARPS + w) * HC_SLICE;  // this slice's staging run
+  u32 run = 0, fsum = 0;
+#pragma unroll
+  for (int j = 0; j < HC16_ROWS_PER_WARP; j++) {
+    const u32 wv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+    u32 f[8]; bool sv[8]; u32 b[8];
+    u32 any = 0, below = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      f[q] = (q & 1) ? (wv[q >> 1] >> 16) : (wv[q >> 1] & 0xFFFFu);
+      fsum += f[q];
+      sv[q] = f[q] >= hmin;
+      b[q] = __ballot_sync(0xffffffffu, sv[q]);
+      any |= b[q]; below += __popc(b[q] & ltmask); tot += __popc(b[q]);
+    }
+    if (any) {
+      u32 o = run + below;
+      const u32 si = (u32)j * 256 + lane * 8;            // slot offset inside the slice
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (sv[q]) { sa.st_idx[sbase + o] = (uint16_t)(si + q); sa.st_cnt[sbase + o] = f[q]; o++; }
+      run += tot;
+    }
+    if (wv[0] | wv[1] | wv[2] | wv[3]) h4[q0 + (u64)j * 32] = make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+  if (lane == 0) {
+    s_agg[w] = run; sa.slice_counts[(u64)c * HC_WARPS + w] = run;
+    if (fsum) atomicAdd((unsigned long long*)(sa.win_sum + wl), (unsigned long long)fsum);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { u32 t = 0; for (int i = 0; i < HC_WARPS; i++) t += s_agg[i]; sa.chunk_counts[c] = t; }
+}
+
 // ---- rolled variant (k <= 32) ---------------------------------------------------------------
 // The search + 128-bit extraction + bit-reversal of the kernel above cost ~60 of its ~155
 // instructions per k-mer.  Here a CTA stages a tile of HR_TILE records in shared memory and
@@ -181,7 +252,7 @@ __device__ __forceinline__ u32 ld_acquire_u32(const u32* p)
 // FUSED: the item stream interleaves, after the tiles of window b, the compact chunks (compact_chunk)
 // of window b - HR_DELAY, whose fill is complete by then (checked on its done counter): the window is
 // swept while it is still L2-resident and the sweep's instructions hide under the RED-bound fill.
-template <bool D32, bool TAIL64, int HR_TILE, bool FUSED>
+template <bool D32, bool TAIL64, int HR_TILE, bool FUSED, bool H16>
 __global__ void __launch_bounds__(HR_THREADS)
 hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ boff, const u32* __restrict__ bcnt,
                       int k, u64 Wbits, FastMod64 fm, FastMod32 fm32, u32* __restrict__ hist, u32 p0, u32 gp, u32* __restrict__ ticket,
@@ -251,7 +322,7 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
   const u32 p = p0 + y;
   const u32 n = bcnt[p];
   const u64 b0 = boff[p];
-  u32* __restrict__ h = hist + (u64)y * Wbits;
+  u32* __restrict__ h = hist + (u64)y * (Wbits >> (H16 ? 1 : 0));
   const u32 tile0 = (item - (FUSED ? bstart(y) : s_pref[y])) * HR_TILE;
   const u32 nt = min((u32)HR_TILE, n - tile0);
   if (tid < 64) s_cnt[tid] = 0;
@@ -312,7 +383,7 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
       const u64 c = f < rc ? f : rc;
       const u64 hv = xxh64_8(c);
       const u64 key = D32 ? (u64)fastmod64_d32(hv, fm32) : fastmod64(hv, fm);
-      if (j < nk) atomicAdd(h + key, 1u);               // result unused -> RED.ADD
+      if (j < nk) hist_inc<H16>(h, key);
       const u64 b = thi >> 62;
       if (TAIL64) thi <<= 2;
       else { thi = (thi << 2) | (tlo >> 62); tlo <<= 2; }
@@ -340,12 +411,14 @@ hash_hist_roll_kernel(const uint4* __restrict__ recs, const u64* __restrict__ bo
 //   hash_scan_kernel     one CTA: exclusive prefix of the chunk counts on top of the running cursor
 //       (bump allocation of the output space, overflow flag, list offsets per window).
 //   hash_copy_kernel     moves every slice's run to its final place as (key u64, count u32).
+template <bool H16>
 __global__ void __launch_bounds__(HC_THREADS, 5)
 hash_compact_kernel(u64 Wbits, u32 nchunks, u32* __restrict__ hist, SweepArgs sa, const u32* __restrict__ bcnt, u32 p0)
 {
   __shared__ u32 s_agg[HC_WARPS];
   for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {       // grid = nchunks, or a persistent grid striding over the chunks
-    compact_chunk<false>(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
+    if (H16) compact_chunk16(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
+    else compact_chunk<false>(c, Wbits, hist, sa, bcnt[p0 + c / sa.CW] != 0, s_agg);
     __syncthreads();
   }
 }
@@ -355,9 +428,12 @@ hash_compact_kernel(u64 Wbits, u32 nchunks, u32* __restrict__ hist, SweepArgs sa
 __global__ void __launch_bounds__(1024)
 hash_scan_kernel(u32 CW, u32 nchunks, u32 p0, const u32* __restrict__ chunk_counts, u64* __restrict__ chunk_off,
                  u64* __restrict__ list_off, const u64* __restrict__ base_in, u64* __restrict__ total_out,
-                 const u64* __restrict__ cap_p, u32* __restrict__ flags)
+                 const u64* __restrict__ cap_p, u32* __restrict__ flags,
+                 const u64* __restrict__ win_sum /* NULL unless 16-bit counters */, const u64* __restrict__ kcnt, u32 gp)
 {
   __shared__ u64 s_warp[32];
+  if (win_sum)                                    // a window whose fields do not add up to its k-mers saw a counter wrap
+    for (u32 wdw = threadIdx.x; wdw < gp; wdw += 1024) if (win_sum[wdw] != kcnt[p0 + wdw]) flags[1] = 1u;
   const u32 per = (nchunks + 1023u) / 1024u;
   const u32 i0 = min(nchunks, threadIdx.x * per), i1 = min(nchunks, i0 + per);
   u64 sum = 0;
@@ -420,7 +496,7 @@ hash_copy_kernel(u64 Wbits, u32 CW, u32 nchunks, const uint16_t* __restrict__ st
 // meta (device): [0],[1] ping-pong running cursor (group g reads [g&1], writes [(g+1)&1]), [2] capacity.
 cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi, u32* hist, u32 hard_min,
                               u32 p0, u32 gp, u32 group_idx, u32* chunk_counts, u64* chunk_off, SweepStage stage, u64* list_off, u64* meta, u32* flags,
-                              u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase)
+                              u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase, bool h16)
 {
   const u32 hmin = hard_min ? hard_min : 1;
   const u32 CW = hash_sweep_chunks_per_window(Wbits);
@@ -428,9 +504,9 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
   const bool roll = c.W == 1 && gp <= HR_MAXWIN && !kmx_env_flag("KMX_HIST_NOROLL");
   // (opt-in: measured SLOWER than fill + separate compact -- 1.37 vs 1.02 ms per 1.2e8 k-mers -- because every
   //  tile needs a __threadfence before its window can be declared filled; kept for experiments)
-  const bool fused = roll && c.max_bcnt != 0 && kmx_env_flag("KMX_HIST_FUSE");
+  const bool fused = roll && c.max_bcnt != 0 && !h16 && kmx_env_flag("KMX_HIST_FUSE");
   SweepArgs sa; sa.CW = CW; sa.hmin = hmin; sa.st_idx = stage.idx; sa.st_cnt = stage.cnt; sa.slice_counts = stage.slice_counts;
-  sa.chunk_counts = chunk_counts; sa.done = stage.done;
+  sa.chunk_counts = chunk_counts; sa.done = stage.done; sa.win_sum = stage.win_sum;
   if (phase == 0) {
     if (c.max_bcnt) {
       FastMod64 fm; fm.d = mod_d; fm.mlo = mod_mlo; fm.mhi = mod_mhi;
@@ -449,18 +525,21 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
         u32* hist_ticket = stage.done + gp;
         cudaError_t me = cudaMemsetAsync(stage.done, 0, ((size_t)gp + 1) * 4, st);    // done[gp] | ticket
         if (me != cudaSuccess) return me;
-#define KMX_ROLL(D, T, TILE, F) hash_hist_roll_kernel<D, T, TILE, F><<<rgrid, HR_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0, gp, hist_ticket, sa)
-#define KMX_ROLL_F(D, T, TILE) do { if (fused) KMX_ROLL(D, T, TILE, true); else KMX_ROLL(D, T, TILE, false); } while (0)
+#define KMX_ROLL(D, T, TILE, F, H) hash_hist_roll_kernel<D, T, TILE, F, H><<<rgrid, HR_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0, gp, hist_ticket, sa)
+#define KMX_ROLL_F(D, T, TILE) do { if (fused) KMX_ROLL(D, T, TILE, true, false); else if (h16) KMX_ROLL(D, T, TILE, false, true); else KMX_ROLL(D, T, TILE, false, false); } while (0)
 #define KMX_ROLL_T(TILE) do { if (d32 && tail64) KMX_ROLL_F(true, true, TILE); else if (d32) KMX_ROLL_F(true, false, TILE); else if (tail64) KMX_ROLL_F(false, true, TILE); else KMX_ROLL_F(false, false, TILE); } while (0)
         if (tile == 512) KMX_ROLL_T(512); else if (tile == 1024) KMX_ROLL_T(1024); else KMX_ROLL_T(256);
 #undef KMX_ROLL_T
 #undef KMX_ROLL_F
 #undef KMX_ROLL
       }
-      else if (c.W == 1 && d32) hash_hist_kernel<1, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
-      else if (c.W == 1) hash_hist_kernel<1, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
-      else if (d32) hash_hist_kernel<2, true><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
-      else hash_hist_kernel<2, false><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0);
+      else {
+#define KMX_HH(WW, D, H) hash_hist_kernel<WW, D, H><<<grid, HH_THREADS, 0, st>>>(recs, c.boff, c.bcnt, c.k, Wbits, fm, f32, hist, p0)
+#define KMX_HH_H(WW, D) do { if (h16) KMX_HH(WW, D, true); else KMX_HH(WW, D, false); } while (0)
+        if (c.W == 1 && d32) KMX_HH_H(1, true); else if (c.W == 1) KMX_HH_H(1, false); else if (d32) KMX_HH_H(2, true); else KMX_HH_H(2, false);
+#undef KMX_HH_H
+#undef KMX_HH
+      }
       *launches += 1;
     }
   } else {
@@ -470,11 +549,15 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
     if (!fused) {
       static const unsigned ccap = []{ const char* v = getenv("KMX_COMPACT_CAP"); int t = v ? atoi(v) : 0; return (unsigned)((t >= 0 && t <= 8) ? t : 0); }();
       const unsigned cgrid = ccap ? std::min<unsigned>(nchunks, 148u * ccap) : nchunks;
-      hash_compact_kernel<<<cgrid, HC_THREADS, 0, st>>>(Wbits, nchunks, hist, sa, c.bcnt, p0);
+      if (h16) {
+        cudaError_t me = cudaMemsetAsync(stage.win_sum, 0, (size_t)gp * 8, st);
+        if (me != cudaSuccess) return me;
+        hash_compact_kernel<true><<<cgrid, HC_THREADS, 0, st>>>(Wbits, nchunks, hist, sa, c.bcnt, p0);
+      } else hash_compact_kernel<false><<<cgrid, HC_THREADS, 0, st>>>(Wbits, nchunks, hist, sa, c.bcnt, p0);
       *launches += 1;
     }
     hash_scan_kernel<<<1, 1024, 0, st>>>(CW, nchunks, p0, chunk_counts, chunk_off, list_off, meta + (group_idx & 1u),
-                                         meta + ((group_idx + 1u) & 1u), meta + 2, flags);
+                                         meta + ((group_idx + 1u) & 1u), meta + 2, flags, h16 ? stage.win_sum : nullptr, c.kcnt, gp);
     hash_copy_kernel<<<(nchunks + HC_WARPS - 1) / HC_WARPS, HC_THREADS, 0, st>>>(Wbits, CW, nchunks, stage.idx, stage.cnt, stage.slice_counts, chunk_counts, chunk_off,
                                                      out_keys, out_counts, win_part, p0, flags);
     *launches += 2;

@@ -109,3 +109,19 @@ def test_hash_mode_larger_sample_all_paths(monkeypatch):
     monkeypatch.setenv("KMX_HIST_FUSE", "1")
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], len(samples))
+
+
+def test_hash_counter_wrap_falls_back_to_32_bit(monkeypatch):
+    """The hash histogram starts with 16-bit counters; a k-mer seen more than 65535 times in one sample
+    (600 poly-A reads = 72000 x A^31) must be detected by the window checksum and the sample redone with
+    32-bit counters -- same bytes as the oracle, and as a run forced to 32-bit counters from the start."""
+    from kmtricks_b200 import synth
+    base = synth.make_fastq(11, 0, 300, L=150, G=5000, d=3e-3, e=3e-3, revcomp=True)
+    polya = b"".join(b"@a%d\n%s\n+\n%s\n" % (i, b"A" * 150, b"I" * 150) for i in range(600))
+    samples = [[base + polya], [synth.make_fastq(11, 1, 300, L=150, G=5000, d=3e-3, e=3e-3, revcomp=True)]]
+    case = dict(k=31, P=4, mode="hash:count:bin", hard_min=1, bloom_size=200_000)
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    monkeypatch.setenv("KMX_HIST32", "1")
+    got32, _ = _run_both(samples, case)
+    assert got32["matrices"] == got["matrices"]

@@ -78,30 +78,39 @@ fq_count_newlines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total /* 
 // single-CTA exclusive scan of tile counts (u32 -> u64 prefix); also total
 __global__ void __launch_bounds__(1024) scan_u32_to_u64(const u32* __restrict__ in, u64* __restrict__ out, u64 n, u64* total)
 {
+  // every thread owns a contiguous range: one round of independent loads, one block scan, one round of stores
   __shared__ u64 s_warp[32];
-  __shared__ u64 s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (u64 base = 0; base < n; base += 1024) {
-    u64 i = base + threadIdx.x;
-    u64 v = (i < n) ? in[i] : 0, x = v;
-    for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      u64 w = s_warp[threadIdx.x], xw = w;
-      for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= o) xw += y; }
-      s_warp[threadIdx.x] = xw - w;
-    }
-    __syncthreads();
-    u64 carry = s_carry;
-    u64 excl = carry + s_warp[threadIdx.x >> 5] + x - v;
-    if (i < n) out[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = excl + v;
-    __syncthreads();
+  const u64 per = (n + 1023) / 1024;
+  const u64 i0 = min(n, (u64)threadIdx.x * per), i1 = min(n, i0 + per);
+  u64 sum = 0;
+  for (u64 i = i0; i < i1; i += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = i + q < i1 ? in[i + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sum += v[q];
   }
-  if (threadIdx.x == 0 && total) *total = s_carry;
+  u64 x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const u64 w = s_warp[threadIdx.x]; u64 xw = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, xw, o); if (threadIdx.x >= (u32)o) xw += y; }
+    s_warp[threadIdx.x] = xw - w;
+  }
+  __syncthreads();
+  u64 run = s_warp[threadIdx.x >> 5] + x - sum;
+  for (u64 i = i0; i < i1; i += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = i + q < i1 ? in[i + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (i + q < i1) { out[i + q] = run; run += v[q]; }
+  }
+  if (threadIdx.x == 1023 && total) *total = run;
 }
 
 // For newline number g (0-based) at text position pos:
@@ -134,38 +143,67 @@ fq_index_lines(const uint4* __restrict__ base, u64 lead, u64 nbytes_total,
   u32 wbase = 0;
   for (int i = 0; i < (int)(threadIdx.x >> 5); i++) wbase += s_warp[i];
   u64 g = tile_prefix[blockIdx.x] + wbase + x - cnt;
-  u32 maxlen = 0;
+  u32 maxlen = 0, bad = 0;
   u64 msk = mask;
+  // Only two of the four newlines of a record need work: #4r (the sequence starts behind it; its end is the
+  // next newline, behind which a '+' must follow) and #4r+3 (an '@' must follow).  The bytes to look at are
+  // independent of each other, so up to FQ_BATCH newlines are located first and their loads issued together.
+  constexpr int FQ_BATCH = 3;
   while (msk) {
-    const int bit = __ffsll((long long)msk) - 1; msk &= msk - 1;
-    const u64 pos = off + bit;
-    const u64 rec = g >> 2; const u32 ph = (u32)(g & 3);
-    g++;
-    if (rec >= nrec) continue;
-    if (ph == 0) {
-      // end of the sequence line = next newline: own mask, then the following threads' masks
-      u64 end;
-      if (msk) end = off + (__ffsll((long long)msk) - 1);
-      else {
-        u32 t = threadIdx.x + 1;
-        while (t < FQ_THREADS && s_mask[t] == 0) t++;
-        if (t < FQ_THREADS) end = tile0 + (u64)t * FQ_BYTES_PER_THREAD + (__ffsll((long long)s_mask[t]) - 1);
-        else {
-          end = tile0 + FQ_TILE;
-          while (end < nbytes_total && bytes[end] != '\n') end++;
-        }
+    u64 a1[FQ_BATCH], a2[FQ_BATCH], e_rec[FQ_BATCH]; u32 e_st[FQ_BATCH], e_len[FQ_BATCH], e_kind[FQ_BATCH];
+#pragma unroll
+    for (int e = 0; e < FQ_BATCH; e++) {          // static slot index: the batch stays in registers
+      e_kind[e] = 9; a1[e] = 0; a2[e] = 0; e_rec[e] = 0; e_st[e] = 0; e_len[e] = 0;
+      bool found = false; u64 pos = 0, rec = 0; u32 ph = 0;
+      while (msk && !found) {
+        const int bit = __ffsll((long long)msk) - 1; msk &= msk - 1;
+        pos = off + bit; rec = g >> 2; ph = (u32)(g & 3);
+        g++;
+        found = rec < nrec && (ph == 0 || ph == 3);
       }
-      const u32 st = (u32)(pos + 1 - lead);
-      u32 len = (u32)(end - (pos + 1));
-      if (len > 1 && bytes[end - 1] == '\r') len--;
-      seq_start[rec] = st; seq_len[rec] = len;
-      maxlen = max(maxlen, len);
-    } else if (ph == 1) {
-      if (pos + 1 < nbytes_total && bytes[pos + 1] != '+') atomicOr(&flags[0], 1u);
-    } else if (ph == 3) {
-      if (pos + 1 < nbytes_total && bytes[pos + 1] != '@') atomicOr(&flags[0], 1u);
+      if (!found) continue;
+      if (ph == 0) {
+        // end of the sequence line = next newline: own mask, then the following threads' masks
+        u64 end;
+        if (msk) end = off + (__ffsll((long long)msk) - 1);
+        else {
+          u32 t = threadIdx.x + 1;
+          while (t < FQ_THREADS && s_mask[t] == 0) t++;
+          if (t < FQ_THREADS) end = tile0 + (u64)t * FQ_BYTES_PER_THREAD + (__ffsll((long long)s_mask[t]) - 1);
+          else {
+            end = tile0 + FQ_TILE;
+            while (end < nbytes_total && bytes[end] != '\n') end++;
+          }
+        }
+        e_kind[e] = 0; e_rec[e] = rec; e_st[e] = (u32)(pos + 1 - lead); e_len[e] = (u32)(end - (pos + 1));
+        a1[e] = end - 1;                        // a trailing '\r' is dropped when the line is longer than 1
+        a2[e] = end + 1;                        // '+' line
+      } else {
+        e_kind[e] = 3; a1[e] = pos + 1;         // '@' of the next record (or end of text)
+      }
+    }
+    u32 b1[FQ_BATCH], b2[FQ_BATCH];
+#pragma unroll
+    for (int e = 0; e < FQ_BATCH; e++) {
+      b1[e] = 0; b2[e] = 0;
+      if (e_kind[e] == 3) { b1[e] = a1[e] < nbytes_total ? bytes[a1[e]] : (u32)'@'; }
+      else if (e_kind[e] == 0) {
+        b1[e] = e_len[e] > 1 ? bytes[a1[e]] : 0u;
+        b2[e] = a2[e] < nbytes_total ? bytes[a2[e]] : (u32)'+';
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < FQ_BATCH; e++) {
+      if (e_kind[e] == 3) bad |= (u32)(b1[e] != '@');
+      else if (e_kind[e] == 0) {
+        const u32 len = e_len[e] - (u32)(b1[e] == '\r');
+        seq_start[e_rec[e]] = e_st[e]; seq_len[e_rec[e]] = len;
+        maxlen = max(maxlen, len);
+        bad |= (u32)(b2[e] != '+');
+      }
     }
   }
+  if (bad) atomicOr(&flags[0], 1u);
   if (blockIdx.x == 0 && threadIdx.x == 0 && bytes[lead] != '@') atomicOr(&flags[0], 1u);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));

@@ -201,23 +201,27 @@ __device__ __forceinline__ void compact_chunk16(u32 c, u64 Wbits, u32* __restric
 #pragma unroll
   for (int j = 0; j < HC16_ROWS_PER_WARP; j++) {
     const u32 wv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-    u32 f[8]; bool sv[8]; u32 b[8];
-    u32 any = 0, below = 0, tot = 0;
+    u32 f[8];
+    u32 smask = 0;                                      // bit q: field q of this lane survives
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       f[q] = (q & 1) ? (wv[q >> 1] >> 16) : (wv[q >> 1] & 0xFFFFu);
       fsum += f[q];
-      sv[q] = f[q] >= hmin;
-      b[q] = __ballot_sync(0xffffffffu, sv[q]);
-      any |= b[q]; below += __popc(b[q] & ltmask); tot += __popc(b[q]);
+      smask |= (u32)(f[q] >= hmin) << q;
     }
-    if (any) {
-      u32 o = run + below;
+    if (__any_sync(0xffffffffu, smask != 0)) {
+      // rank = survivors of the lower lanes (lane-major slot order) + own earlier fields: one shuffle scan of the
+      // per-lane counts instead of one ballot per field
+      const u32 cl = __popc(smask);
+      u32 x = cl;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (u32)o) x += y; }
+      u32 o = run + x - cl;
       const u32 si = (u32)j * 256 + lane * 8;            // slot offset inside the slice
 #pragma unroll
       for (int q = 0; q < 8; q++)
-        if (sv[q]) { sa.st_idx[sbase + o] = (uint16_t)(si + q); sa.st_cnt[sbase + o] = f[q]; o++; }
-      run += tot;
+        if ((smask >> q) & 1u) { sa.st_idx[sbase + o] = (uint16_t)(si + q); sa.st_cnt[sbase + o] = f[q]; o++; }
+      run += __shfl_sync(0xffffffffu, x, 31);
     }
     if (wv[0] | wv[1] | wv[2] | wv[3]) h4[q0 + (u64)j * 32] = make_uint4(0, 0, 0, 0);
   }
@@ -437,7 +441,13 @@ hash_scan_kernel(u32 CW, u32 nchunks, u32 p0, const u32* __restrict__ chunk_coun
   const u32 per = (nchunks + 1023u) / 1024u;
   const u32 i0 = min(nchunks, threadIdx.x * per), i1 = min(nchunks, i0 + per);
   u64 sum = 0;
-  for (u32 i = i0; i < i1; i++) sum += chunk_counts[i];
+  for (u32 i = i0; i < i1; i += 8) {              // 8 independent loads in flight, then the adds
+    u32 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = i + q < i1 ? chunk_counts[i + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sum += v[q];
+  }
   u64 x = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
@@ -451,10 +461,18 @@ hash_scan_kernel(u32 CW, u32 nchunks, u32 p0, const u32* __restrict__ chunk_coun
   }
   __syncthreads();
   u64 run = *base_in + s_warp[threadIdx.x >> 5] + x - sum;
-  for (u32 i = i0; i < i1; i++) {
-    chunk_off[i] = run;
-    if (i % CW == 0) list_off[p0 + i / CW] = run;
-    run += chunk_counts[i];
+  for (u32 i = i0; i < i1; i += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = i + q < i1 ? chunk_counts[i + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      if (i + q < i1) {
+        chunk_off[i + q] = run;
+        if ((i + q) % CW == 0) list_off[p0 + (i + q) / CW] = run;
+        run += v[q];
+      }
+    }
   }
   if (threadIdx.x == 1023) {                      // its range ends at nchunks: run is the grand total
     *total_out = run;

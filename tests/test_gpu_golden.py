@@ -106,3 +106,38 @@ def test_run_samples_lanes_equal_single_lane_and_properties():
         digests.append(hsh.hexdigest())
         eng.close()
     assert digests[0] == digests[1]
+
+
+def test_full_size_sample_conserves_every_kmer(monkeypatch):
+    """One sample launch of BASELINE cfg2's exact shape (1M reads x 150 nt, k=31, P=64, Bloom 2e8) with hard-min 1:
+    the counts of all 64 hash lists must add up to the number of k-mers (nothing lost or double counted anywhere
+    between the FASTQ text and the lists), lists ascending and inside their window; the 16-bit-counter histogram
+    and the 32-bit one must give the same bytes."""
+    import ctypes as C
+    from kmtricks_b200 import engine, synth
+    R, Lr, P = 1_000_000, 150, 64
+    cfg = engine.Config(kmer_size=31, nb_partitions=P, mode="hash:bf:bin", hard_min=1, bloom_size=200_000_000)
+    digests = []
+    for force32 in (False, True):
+        if force32:
+            monkeypatch.setenv("KMX_HIST32", "1")
+        eng = engine.Engine(cfg, 1); L = eng.lib; h = eng.h
+        sb = R * synth.record_bytes(Lr)
+        d = C.c_void_p(); assert L.kmx_dev_alloc(h, sb + 64, C.byref(d)) == 0
+        assert L.kmx_synth_fastq(h, 1234, 0, 0, R, Lr, 5_000_000, 2e-3, 2e-3, 1, d.value) == 0
+        ptrs = (C.c_void_p * 1)(d.value); sizes = (C.c_size_t * 1)(sb); hm = (C.c_uint32 * 1)(1)
+        pin = np.zeros((1, P), dtype=np.uint64)
+        rc = L.kmx_run_samples(h, 1, ptrs, sizes, 1, None, hm, 1, pin.ctypes.data_as(C.POINTER(C.c_uint64)))
+        assert rc == 0, L.kmx_last_error(h)
+        assert int(pin.sum()) == R * (Lr - 31 + 1)
+        W = cfg.window_bits
+        hsh = hashlib.sha256()
+        for p in range(P):
+            keys, cnt = eng.counts(0, p)
+            assert int(cnt.astype(np.uint64).sum()) == int(pin[0, p]), f"partition {p}: counts do not add up to its k-mers"
+            assert (np.diff(keys.astype(np.int64)) > 0).all()
+            assert keys.min(initial=W * p) >= W * p and keys.max(initial=W * p) < W * (p + 1)
+            hsh.update(keys.tobytes()); hsh.update(cnt.tobytes())
+        digests.append(hsh.hexdigest())
+        eng.close()
+    assert digests[0] == digests[1]

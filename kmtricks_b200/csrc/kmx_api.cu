@@ -2,6 +2,7 @@
 #include "../../include/kmx.h"
 #include "common.cuh"
 #include "kmx_internal.h"
+#include "s1_v5.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -422,7 +423,10 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
     a.cursor = ln->d_cursor; a.kcnt = ln->d_kcnt; a.overflow = ln->d_flags + 2;
     a.pack_words = (max_len + 15) / 16; if (a.pack_words < 1) a.pack_words = 1;
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
-    { PROF(KMX_PROF_S1); CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
+    { PROF(KMX_PROF_S1);
+      s1v5::Geo geo; size_t smem5 = 0;
+      if (s1_v5_usable(max_len, a.k, a.m, P, &geo, &smem5)) CK(launch_s1_v5(ctx->W, a, geo, smem5, ln->st, &ln->launches));
+      else CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
     u64* kc = (u64*)ln->h_pin; u32* cur = (u32*)(ln->h_pin + P * 8); u32* ovf = (u32*)(ln->h_pin + P * 12);
     CK(cudaMemcpyAsync(kc, ln->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ln->st));
     CK(cudaMemcpyAsync(cur, ln->d_cursor, P * 4, cudaMemcpyDeviceToHost, ln->st));

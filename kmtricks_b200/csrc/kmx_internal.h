@@ -39,6 +39,10 @@ cudaError_t launch_fq_index(const uint8_t* text, u64 nbytes, u32* tile_counts, u
                             u64* d_total, u32* seq_start, u32* seq_len, u64 nrec_cap, u32* flags,
                             int phase, cudaStream_t st, u64* launches);
 cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches);
+// position-parallel variant for short reads (s1_v5.cu)
+namespace s1v5 { struct Geo; }
+bool s1_v5_usable(u32 max_len, int k, int m, u32 P, s1v5::Geo* geo, size_t* smem);
+cudaError_t launch_s1_v5(int W, const S1Args& a, const s1v5::Geo& geo, size_t smem, cudaStream_t st, u64* launches);
 
 // ---- stage 2 (s2_count.cu) --------------------------------------------------------------
 struct S2Common {

@@ -90,12 +90,32 @@ def test_many_samples_many_partitions(name, case, N):
     ("KMX_HIST_FUSE", "hash_count"),
     ("KMX_NO_HT", "kmer_count"),           # generic path: expand -> segmented radix sort -> run-length (fallback of the hash-count)
     ("KMX_NO_HT", "k63_kmer_pa"),
+    ("KMX_S1V5_OFF", "kmer_count"),        # stage 1 by the streaming thread-per-read kernel (what long sequences use)
+    ("KMX_S1V5_OFF", "k63_kmer_pa"),
+    ("KMX_S1V5_OFF", "hash_bf"),
 ])
 def test_fallback_paths_stay_exact(flag, name, synth_samples, monkeypatch):
     """The alternative stage-2 paths behind the environment switches give the same bytes as the default ones."""
     monkeypatch.setenv(flag, "1")
     got, want = _run_both(synth_samples, CASES[name])
     _compare(got, want, CASES[name]["P"], len(synth_samples))
+
+
+def test_stage1_streaming_kernel_edge_cases(edge_samples, monkeypatch):
+    """The edge-case inputs through the streaming stage-1 kernel as well (the default for short reads is the
+    position-parallel one)."""
+    monkeypatch.setenv("KMX_S1V5_OFF", "1")
+    got, want = _run_both(edge_samples, CASES["kmer_count"])
+    _compare(got, want, CASES["kmer_count"]["P"], len(edge_samples))
+
+
+@pytest.mark.parametrize("R", [16, 64, 128])
+def test_stage1_position_parallel_reads_per_cta(R, synth_samples, edge_samples, monkeypatch):
+    """Other CTA geometries of the position-parallel stage-1 kernel (reads per CTA)."""
+    monkeypatch.setenv("KMX_S1V5_R", str(R))
+    for samples in (synth_samples, edge_samples):
+        got, want = _run_both(samples, CASES["kmer_count"])
+        _compare(got, want, CASES["kmer_count"]["P"], len(samples))
 
 
 def test_hash_mode_larger_sample_all_paths(monkeypatch):

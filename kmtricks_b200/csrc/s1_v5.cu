@@ -101,23 +101,28 @@ s1_superk_v5(const S1Args a, const Geo geo)
       if (end <= first) { if (tid == 0) *a.overflow = 1u; return; }       // fail loudly through the host's retry limit
     }
     const u32 nev = x.pfx[end] - base;
-    // ---- P3c: one event per thread
-    for (u32 e = tid; e < nev; e += V5_THREADS) {
-      const u32 t = event_item(x.pfx, first, end, base, e);
+    // ---- P3c: the events of one item per thread, then (P4 pass 1) their partition, per-partition rank and k-mer totals
+    for (u32 t = first + tid; t < end; t += V5_THREADS) {
+      const u32 s0 = x.pfx[t] - base, n = x.pfx[t + 1] - x.pfx[t];
+      if (!n) continue;
       const u32 r = item_read(geo, t);
-      if (!x.inval[r]) p3_emit(x, r, t - r * geo.nblk, e - (x.pfx[t] - base), e);
-    }
-    for (u32 r = tid; r < R; r += V5_THREADS) {      // reads with invalid bases: per-k-mer walk
-      const u32 t = r * geo.nblk;
-      if (x.inval[r] && x.len[r] && t >= first && t < end) p3_slow<true>(x, r, x.len[r], x.pfx[t] - base);
-    }
-    __syncthreads();
-    // ---- P4 pass 1: per-partition rank of every event, k-mer totals
-    for (u32 q = tid; q < nev; q += V5_THREADS) {
-      const Ev e = x.ev[q];
-      const u32 p = __ldg(a.repart + e.y);          // Repartitor, PartiInfo.hpp:381
-      x.ev[q].y = p | (atomicAdd(&x.hist[p], 1u) << 16);
-      atomicAdd(&x.kc[p], (e.x >> 19) & 127u);
+      if (!x.inval[r]) p3_emit_item(x, r, t - r * geo.nblk, s0);
+      else p3_slow<true>(x, r, x.len[r], s0);       // reads with invalid bases: per-k-mer walk (all their events sit in block 0's item)
+      u32 q = s0;
+      for (; q + 2 <= s0 + n; q += 2) {
+        const Ev e0 = x.ev[q], e1 = x.ev[q + 1];
+        const u32 p0 = __ldg(a.repart + e0.y), p1 = __ldg(a.repart + e1.y);     // Repartitor, PartiInfo.hpp:381
+        x.ev[q].y = p0 | (atomicAdd(&x.hist[p0], 1u) << 16);
+        x.ev[q + 1].y = p1 | (atomicAdd(&x.hist[p1], 1u) << 16);
+        atomicAdd(&x.kc[p0], (e0.x >> 19) & 127u);
+        atomicAdd(&x.kc[p1], (e1.x >> 19) & 127u);
+      }
+      if (q < s0 + n) {
+        const Ev e0 = x.ev[q];
+        const u32 p0 = __ldg(a.repart + e0.y);
+        x.ev[q].y = p0 | (atomicAdd(&x.hist[p0], 1u) << 16);
+        atomicAdd(&x.kc[p0], (e0.x >> 19) & 127u);
+      }
     }
     __syncthreads();
     for (u32 p = tid; p < a.P; p += V5_THREADS) {

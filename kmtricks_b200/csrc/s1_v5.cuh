@@ -133,14 +133,6 @@ KMX_HD u32 item_read(const Geo& g, u32 t)
   return (u32)(((u64)t * g.inv_nblk) >> 32);
 #endif
 }
-// item of event e: the largest t in [first, end) with pfx[t] - base <= e
-KMX_HD u32 event_item(const u32* pfx, u32 first, u32 end, u32 base, u32 e)
-{
-  u32 lo = first, hi = end;
-  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (pfx[mid] - base <= e) lo = mid; else hi = mid; }
-  return lo;
-}
-
 struct Ev { u32 x, y; };   // x = read | (base index just past the record) << 7 | (#k-mers) << 19 ; y = minimizer, later partition | rank << 16
 
 struct Cta {
@@ -233,19 +225,27 @@ KMX_HD void p1_row(const Cta& x, u32 r, u32 lane, u32 nm)
   const u32* be = x.BE + r * x.g.LW + 2 * (lane >> 4);
   const u32* le = x.LE + r * x.g.LW + 2 * (lane >> 4);
   u32* u = x.U + r * x.g.Lpad + lane;
-#ifdef __CUDA_ARCH__
-#pragma unroll 2
-#endif
-  for (u32 a = lane; a < nm; a += 32, be += 4, le += 4, u += 32) {
-    u32 b0w, b1w, l0w, l1w;
-    ld2(be, b0w, b1w); ld2(le, l0w, l1w);
-    const u32 fm = fsl(b1w, b0w, q2) >> sh;              // bases a .. a+m-1, first base most significant
-    const u32 rm = fsr(l0w, l1w, q2) & mmask;            // its reverse complement
-    const u32 canon = umin(fm, rm);
-    u32 t = ~(canon | (canon >> 2));
-    t = ((t >> 1) & t) & ban;                            // "AA" anywhere but at the two leading bases (Model.hpp:1220-1251)
-    *u = t ? mmask : canon;
+  u32 a = lane;
+#define KMX_P1_ONE(I)                                                                                   \
+  {                                                                                                     \
+    u32 b0w, b1w, l0w, l1w;                                                                             \
+    ld2(be + 4 * (I), b0w, b1w); ld2(le + 4 * (I), l0w, l1w);                                           \
+    const u32 fm = fsl(b1w, b0w, q2) >> sh;       /* bases a .. a+m-1, first base most significant */   \
+    const u32 rm = fsr(l0w, l1w, q2) & mmask;     /* its reverse complement */                          \
+    const u32 canon = umin(fm, rm);                                                                     \
+    u32 t = ~(canon | (canon >> 2));                                                                    \
+    t = ((t >> 1) & t) & ban;                     /* "AA" anywhere but at the two leading bases (Model.hpp:1220-1251) */ \
+    u[32 * (I)] = t ? mmask : canon;                                                                    \
   }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (; a + 96 < nm; a += 128, be += 16, le += 16, u += 128) { KMX_P1_ONE(0) KMX_P1_ONE(1) KMX_P1_ONE(2) KMX_P1_ONE(3) }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (; a < nm; a += 32, be += 4, le += 4, u += 32) KMX_P1_ONE(0)
+#undef KMX_P1_ONE
 }
 
 // ---- P2: block g of read r: minimizers of k-mers [g w, g w + w) and their change mask ----
@@ -404,26 +404,29 @@ KMX_HD u32 p3_count(const Cta& x, u32 r, u32 g, u32 len)
   while (last > x.max_nk) { last -= x.max_nk; n++; }
   return n;
 }
-// P3c, one event per item: event j of item (r, g) -> x.ev[slot].  (Reads with invalid bases are
-// emitted by p3_slow<true>, one thread per read.)
-KMX_HD void p3_emit(const Cta& x, u32 r, u32 g, u32 j, u32 slot)
+// P3c, item (r, g): its events -> x.ev[slot ...] in k-mer order, y = minimizer.  (Reads with invalid
+// bases are emitted by p3_slow<true>, one thread per read.)
+KMX_HD void p3_put(const Cta& x, u32 slot, u32 r, u32 s, u32 e, u32 mz)
 {
-  const u32 w = (u32)x.w, lo = g * w;
+  Ev ev; ev.x = r | ((e + (u32)x.k - 1u) << 7) | ((e - s) << 19); ev.y = mz;
+  x.ev[slot] = ev;
+}
+KMX_HD void p3_emit_item(const Cta& x, u32 r, u32 g, u32 slot)
+{
+  const u32 lo = g * (u32)x.w;
   const u32* M = x.S + r * x.g.Spad;
   const u32* ch = x.CH + 2 * (r * x.g.nblk + g);
   u64 mask = (u64)ch[0] | ((u64)ch[1] << 32);
-  const u32 c = popc64(mask);
-  u32 s, e, mzpos;
-  if (j + 1 < c) {
-    for (u32 i = 0; i < j; i++) mask &= mask - 1;
-    s = lo + ctz64(mask); mask &= mask - 1; e = lo + ctz64(mask); mzpos = s;
-  } else {
-    const u32 pl = lo + 63u - clz64(mask);
-    const u32 nxt = x.NX[r * x.g.nblk + g];
-    s = pl + (j - (c - 1u)) * x.max_nk; e = umin(s + x.max_nk, nxt); mzpos = pl;
+  if (!mask) return;
+  const u32 nxt = x.NX[r * x.g.nblk + g];
+  u32 prev = lo + ctz64(mask); mask &= mask - 1;
+  while (mask) {
+    const u32 t = lo + ctz64(mask); mask &= mask - 1;
+    p3_put(x, slot++, r, prev, t, M[prev]);
+    prev = t;
   }
-  Ev ev; ev.x = r | ((e + (u32)x.k - 1u) << 7) | ((e - s) << 19); ev.y = M[mzpos];
-  x.ev[slot] = ev;
+  const u32 mz = M[prev];
+  for (u32 s0 = prev; s0 < nxt; s0 += x.max_nk) p3_put(x, slot++, r, s0, umin(s0 + x.max_nk, nxt), mz);
 }
 
 // ---- P4: the record of one event: nb = k + nk - 1 bases ending just before base `iend` ------

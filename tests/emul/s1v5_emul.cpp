@@ -145,12 +145,11 @@ int main(int argc, char** argv)
       if (end == first) { fprintf(stderr, "item with %u events does not fit\n", cnt[first]); return 1; }
       const uint32_t acc = x.pfx[end] - base;
       for (uint32_t q = 0; q < acc; q++) { x.ev[q].x = 0xFFFFFFFFu; x.ev[q].y = 0xFFFFFFFFu; }
-      for (uint32_t e = 0; e < acc; e++) {                      // as the kernel: binary search of the item of event e
-        const uint32_t t = event_item(x.pfx, first, end, base, e), r = item_read(x.g, t);
+      for (uint32_t t = first; t < end; t++) {                  // as the kernel: one item per thread
+        const uint32_t r = item_read(x.g, t);
         if (r != t / x.g.nblk) { fprintf(stderr, "item_read(%u) = %u\n", t, r); return 1; }
-        if (cnt[t] == 0 || e - (x.pfx[t] - base) >= cnt[t]) { fprintf(stderr, "search landed on the wrong item\n"); return 1; }
-        if (x.inval[r]) continue;
-        p3_emit(x, r, t % x.g.nblk, e - (x.pfx[t] - base), e);
+        if (!cnt[t] || x.inval[r]) continue;
+        p3_emit_item(x, r, t % x.g.nblk, x.pfx[t] - base);
       }
       for (uint32_t r = 0; r < R; r++) {
         const uint32_t t = r * x.g.nblk;

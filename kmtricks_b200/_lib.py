@@ -69,6 +69,7 @@ SYMBOLS = {
     "kmx_profile_reset": (_i, [_vp]),
     "kmx_profile_get": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "kmx_device_bytes": (_u64, [_vp]),
+    "kmx_stat": (_u64, [_vp, _i]),
 }
 
 _lib = None

@@ -79,7 +79,7 @@ struct Lane {
   std::string err;
   u64 launches = 0;
   // ---- stage 1
-  DBuf text, seq_start, seq_len, tile_counts, tile_prefix, nlmask;
+  DBuf text, seq_start, seq_len, tile_counts, tile_prefix, nlmask, cta_tile;
   u64* d_total = nullptr;          // 1 u64
   u32* d_flags = nullptr;          // [0] fmt error [1] max len [2] overflow
   DBuf records;                    // bucket slab
@@ -108,6 +108,8 @@ struct kmx_ctx {
   int hist_ok = -1;
   bool hist16 = true;              // hash histogram with 16-bit counters until one wraps (count_hash_hist)
   int active_lanes = 1;            // lanes running concurrently (sizes the L2-resident histogram groups)
+  std::atomic<u64> stat[KMX_STAT_KINDS];
+  u32 s1_len_hint = 0;             // longest FASTQ read seen so far: geometry of the self-indexing stage-1 launch (0 = none yet)
   double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
   bool ht_union_ok = true;
   bool prof_on = false;
@@ -243,7 +245,7 @@ static void lane_destroy(Lane* ln)
   kmx_ctx* ctx = ln->ctx;
   if (ln->st) cudaStreamSynchronize(ln->st);
   DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->nlmask, &ln->records, &ln->hist,
-                  &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
+                  &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->cta_tile, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
   for (void* p : singles) if (p) cudaFree(p);
@@ -259,6 +261,7 @@ extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
   if (!prm || !out) return KMX_ERR_ARG;
   *out = nullptr;
   kmx_ctx* ctx = new kmx_ctx();
+  for (auto& v : ctx->stat) v = 0;
   *out = ctx;                                   // returned even on failure so the caller can read the error
   ctx->device = device; ctx->prm = *prm;
   Lane tmp; tmp.ctx = ctx; Lane* ln = &tmp;     // error sink until lane 0 exists
@@ -321,6 +324,7 @@ extern "C" uint64_t kmx_launch_count(const kmx_ctx* ctx)
   return t;
 }
 extern "C" uint64_t kmx_device_bytes(const kmx_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
+extern "C" uint64_t kmx_stat(const kmx_ctx* ctx, int which) { return (ctx && which >= 0 && which < KMX_STAT_KINDS) ? ctx->stat[which].load() : 0; }
 extern "C" void* kmx_stream(kmx_ctx* ctx) { return (ctx && !ctx->lanes.empty()) ? (void*)ctx->lanes[0]->st : nullptr; }
 extern "C" int kmx_sync(kmx_ctx* ctx)
 {
@@ -402,7 +406,9 @@ static int superk_begin(Lane* ln)
 
 // run stage 1 over nseg segments described by (d_start, d_len) into the buckets; retries
 // with exact capacities when a bucket overflowed.
-static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers, u32 max_len)
+static const int KMX_S1_FALLBACK = -1001;   // internal: the self-indexing launch met a longer read or a format problem; redo with the line index
+static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_start, const u32* d_len, u64 nseg, u64 est_kmers, u32 max_len,
+                  const S1Idx* fi = nullptr)
 {
   if (max_len > 2048) return fail(ln, KMX_ERR_FORMAT, "sequence of %u bases: stage 1 takes segments of <= 2048 bases (kmx_superk_push_reads splits long sequences)", max_len);
   kmx_ctx* ctx = ln->ctx;
@@ -415,7 +421,8 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
     if (rc) return rc;
     rc = upload_bucket_meta(ln);
     if (rc) return rc;
-    CK(cudaMemsetAsync(ln->d_flags + 2, 0, 4, ln->st));
+    if (fi) CK(cudaMemsetAsync(ln->d_flags, 0, 16, ln->st));
+    else CK(cudaMemsetAsync(ln->d_flags + 2, 0, 4, ln->st));
     S1Args a;
     a.text = d_text; a.text_bytes = text_bytes; a.seg_start = d_start; a.seg_len = d_len; a.nseg = nseg;
     a.k = (int)ctx->prm.kmer_size; a.m = (int)ctx->prm.minim_size; a.wlen = ctx->wlen; a.max_nk = ctx->max_nk;
@@ -425,13 +432,19 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
     { PROF(KMX_PROF_S1);
       s1v5::Geo geo; size_t smem5 = 0;
-      if (s1_v5_usable(max_len, a.k, a.m, P, &geo, &smem5)) CK(launch_s1_v5(ctx->W, a, geo, smem5, ln->st, &ln->launches));
+      if (fi) {
+        if (!s1_v5_usable(max_len, a.k, a.m, P, &geo, &smem5) || geo.R != S1_FUSED_R) return KMX_S1_FALLBACK;
+        CK(launch_s1_v5(ctx->W, a, geo, smem5, fi, ln->st, &ln->launches));
+      } else if (s1_v5_usable(max_len, a.k, a.m, P, &geo, &smem5)) CK(launch_s1_v5(ctx->W, a, geo, smem5, nullptr, ln->st, &ln->launches));
       else CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
     u64* kc = (u64*)ln->h_pin; u32* cur = (u32*)(ln->h_pin + P * 8); u32* ovf = (u32*)(ln->h_pin + P * 12);
     CK(cudaMemcpyAsync(kc, ln->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ln->st));
     CK(cudaMemcpyAsync(cur, ln->d_cursor, P * 4, cudaMemcpyDeviceToHost, ln->st));
+    u32* fl4 = (u32*)(ln->h_pin + P * 12 + 16);
     CK(cudaMemcpyAsync(ovf, ln->d_flags + 2, 4, cudaMemcpyDeviceToHost, ln->st));
+    if (fi) CK(cudaMemcpyAsync(fl4, ln->d_flags, 16, cudaMemcpyDeviceToHost, ln->st));
     CK(cudaStreamSynchronize(ln->st));
+    if (fi && (fl4[0] || fl4[3])) return KMX_S1_FALLBACK;     // the device cursors are restored from the host snapshot by the next upload
     if (!*ovf) { ln->h_cursor.assign(cur, cur + P); ln->h_kcnt.assign(kc, kc + P); return KMX_OK; }
     // exact sizes are now known (the cursors kept counting); redo this push from the snapshot
     for (u32 p = 0; p < P; p++) need[p] = (u64)cur[p] + 64;
@@ -464,6 +477,22 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   if (nlines % 4) return fail(ln, KMX_ERR_FORMAT, "FASTQ block has %llu lines (not a multiple of 4)", (unsigned long long)nlines);
   const u64 nrec = nlines / 4;
   if (nrec == 0) return KMX_OK;
+  // Self-indexing launch: once the read length of this run is known (from an earlier block), stage 1 finds its reads in the
+  // newline masks itself -- no line-index pass, no seq_start / seq_len arrays.  A longer read or a format problem sends the
+  // block through the indexed path below (which also reports the error).
+  u32 hint;
+  { std::lock_guard<std::mutex> g(ln->ctx->mu); hint = ln->ctx->s1_len_hint; }
+  if (hint && !kmx_env_flag("KMX_S1_NOFUSE")) {
+    const u64 ncta = (nrec + S1_FUSED_R - 1) / S1_FUSED_R;
+    CK(ensure(ln, ln->cta_tile, ncta * 4));
+    { PROF(KMX_PROF_INDEX); CK(launch_fq_cta_pos((const u64*)ln->nlmask.p, (const u64*)ln->tile_prefix.p, ntiles, (u32*)ln->cta_tile.p, ncta, ln->st, &ln->launches)); }
+    S1Idx fi;
+    const uintptr_t ta = reinterpret_cast<uintptr_t>(d_text);
+    fi.nlmask64 = (const u64*)ln->nlmask.p; fi.cta_pos = (const u32*)ln->cta_tile.p;
+    fi.ntiles = ntiles; fi.lead = ta & 15; fi.tot = fi.lead + nbytes; fi.flags = ln->d_flags; fi.geo_maxlen = hint;
+    const int rc = run_s1(ln, d_text, nbytes, nullptr, nullptr, nrec, nbytes / 2, hint, &fi);
+    if (rc != KMX_S1_FALLBACK) { if (rc == KMX_OK) ln->ctx->stat[KMX_STAT_S1_SELF_INDEXED]++; return rc; }
+  }
   CK(ensure(ln, ln->seq_start, nrec * 4));
   CK(ensure(ln, ln->seq_len, nrec * 4));
   CK(cudaMemsetAsync(ln->d_flags, 0, 8, ln->st));
@@ -473,7 +502,10 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   CK(cudaMemcpyAsync(fl, ln->d_flags, 8, cudaMemcpyDeviceToHost, ln->st));
   CK(cudaStreamSynchronize(ln->st));
   if (fl[0]) return fail(ln, KMX_ERR_FORMAT, "text is not strict 4-line FASTQ");
-  return run_s1(ln, d_text, nbytes, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, nrec, nbytes / 2, fl[1]);
+  const u32 block_max = fl[1];
+  ln->ctx->stat[KMX_STAT_S1_INDEXED]++;
+  { std::lock_guard<std::mutex> g(ln->ctx->mu); ln->ctx->s1_len_hint = std::max(ln->ctx->s1_len_hint, block_max); }
+  return run_s1(ln, d_text, nbytes, (const u32*)ln->seq_start.p, (const u32*)ln->seq_len.p, nrec, nbytes / 2, block_max);
 }
 
 static int superk_push_reads(Lane* ln, const char* seqs, const uint64_t* off, size_t nseq)

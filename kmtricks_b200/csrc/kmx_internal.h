@@ -42,7 +42,19 @@ cudaError_t launch_s1(int W, const S1Args& a, cudaStream_t st, u64* launches);
 // position-parallel variant for short reads (s1_v5.cu)
 namespace s1v5 { struct Geo; }
 bool s1_v5_usable(u32 max_len, int k, int m, u32 P, s1v5::Geo* geo, size_t* smem);
-cudaError_t launch_s1_v5(int W, const S1Args& a, const s1v5::Geo& geo, size_t smem, cudaStream_t st, u64* launches);
+// idx == NULL: reads given by a.seg_start / a.seg_len.  Otherwise the kernel finds its own reads in the
+// newline masks of the FASTQ count pass (no line-index pass, no seq_start / seq_len arrays): a.nseg = records
+static const u32 FQ_TILE_BYTES = 16384;        // text bytes per tile of the count pass (256 threads x 64 bytes)
+static const u32 S1_FUSED_R = 32;              // reads per CTA of the self-indexing launch
+struct S1Idx {
+  const u64* nlmask64;        // one bit per text byte, whole tiles, in the coordinates of the 16-byte-aligned base below the text
+  const u32* cta_pos;         // [ceil(nrec / S1_FUSED_R)] position (mask coordinates) of newline number 4 * S1_FUSED_R * cta
+  u64 ntiles, lead, tot;      // tot = lead + text bytes
+  u32* flags;                 // [0] not strict 4-line FASTQ, [3] a read is longer than the launch geometry
+  u32 geo_maxlen;
+};
+cudaError_t launch_s1_v5(int W, const S1Args& a, const s1v5::Geo& geo, size_t smem, const S1Idx* idx, cudaStream_t st, u64* launches);
+cudaError_t launch_fq_cta_pos(const u64* nlmask64, const u64* tile_prefix, u64 ntiles, u32* cta_pos, u64 ncta, cudaStream_t st, u64* launches);
 
 // ---- stage 2 (s2_count.cu) --------------------------------------------------------------
 struct S2Common {

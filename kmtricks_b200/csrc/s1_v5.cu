@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "kmx_internal.h"
 #include "s1_v5.cuh"
+#include <cstring>
+#include <cstdlib>
 
 namespace kmx {
 
@@ -12,9 +14,39 @@ using namespace s1v5;
 static constexpr int V5_THREADS = 256;
 static constexpr int V5_WARPS = V5_THREADS / 32;
 
-template <int W>
+// byte position (in the coordinates of the mask array) of newline number 4 * S1_FUSED_R * c, for every CTA c of the
+// self-indexing launch.  One warp per 16 KiB tile: 8 x 32 mask words, ranked by popcount + warp scan.
+__global__ void __launch_bounds__(256)
+fq_cta_pos(const u64* __restrict__ nlmask64, const u64* __restrict__ tile_prefix, u64 ntiles, u32* __restrict__ cta_pos, u64 ncta)
+{
+  const u32 lane = threadIdx.x & 31u;
+  const u64 t = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= ntiles) return;
+  const u64 per = 4ull * S1_FUSED_R;
+  u64 g = tile_prefix[t];
+  u64 m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = nlmask64[t * 256 + (u64)i * 32 + lane];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const u32 cnt = (u32)__popcll(m[i]);
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += y; }
+    const u64 gg = g + inc - cnt;                         // number of this word's first newline
+    const u64 c = (gg + per - 1) / per;                   // a word holds <= 64 newlines: at most one multiple of 128
+    if (cnt && c * per < gg + cnt && c < ncta) {
+      u64 mm = m[i];
+      for (u32 j = (u32)(c * per - gg); j; j--) mm &= mm - 1;
+      cta_pos[c] = (u32)((t * 256 + (u64)i * 32 + lane) * 64 + (u32)(__ffsll((long long)mm) - 1));
+    }
+    g += __shfl_sync(0xffffffffu, inc, 31);
+  }
+}
+
+template <int W, bool FUSED>
 __global__ void __launch_bounds__(V5_THREADS)
-s1_superk_v5(const S1Args a, const Geo geo)
+s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
 {
   extern __shared__ __align__(16) u32 smem5[];
   __shared__ u32 s_end;
@@ -29,12 +61,79 @@ s1_superk_v5(const S1Args a, const Geo geo)
   const u64 seg0 = (u64)blockIdx.x * R;
 
   for (u32 p = tid; p < a.P; p += V5_THREADS) { x.hist[p] = 0; x.kc[p] = 0; }
-  for (u32 r = tid; r < R; r += V5_THREADS) {
-    const u64 seg = seg0 + r;
-    u32 len = 0, st = 0;
-    if (seg < a.nseg) { len = a.seg_len[seg]; st = a.seg_start[seg]; }
-    if (len < (u32)a.k) len = 0;                  // Sequence2SuperKmer.hpp:143-144
-    x.len[r] = len; x.start[r] = st; x.inval[r] = 0;
+  u32 nr = 0, bad = 0, vplus = '+', vat = '@';       // self-indexing launch: format checks, consumed after P0 (their loads overlap it)
+  if (!FUSED) {
+    for (u32 r = tid; r < R; r += V5_THREADS) {
+      const u64 seg = seg0 + r;
+      u32 len = 0, st = 0;
+      if (seg < a.nseg) { len = a.seg_len[seg]; st = a.seg_start[seg]; }
+      if (len < (u32)a.k) len = 0;                  // Sequence2SuperKmer.hpp:143-144
+      x.len[r] = len; x.start[r] = st; x.inval[r] = 0;
+    }
+  } else {
+    // The CTA's reads are records [32 c, 32 c + 32) of the strict 4-line FASTQ text: newline number 4 i ends the header of
+    // record i, 4 i + 1 its sequence, 4 i + 3 the record.  Warp 0 ranks the newline masks of the count pass from the
+    // position the host-launched table gives for the CTA's first newline (256 mask words = 16 KiB of text per round).
+    u32* s_nl = x.U;                                   // [4 * S1_FUSED_R]; U is not written before P1
+    nr = (u32)min((u64)S1_FUSED_R, a.nseg - seg0);
+    const u32 need = 4 * nr;
+    for (u32 i = tid; i < 4 * S1_FUSED_R; i += V5_THREADS) s_nl[i] = 0xFFFFFFFFu;      // "no such newline" (end of text)
+    __syncthreads();
+    {
+      // every thread ranks one mask word of a 256-word (16 KiB) window per round: popcount, warp scan, warp totals through
+      // shared memory; a window holds the 4 x 32 newlines of a CTA unless records are longer than 512 bytes
+      u32* s_wsum = x.U + 4 * S1_FUSED_R;              // [2][V5_WARPS] (double-buffered: one barrier per round)
+      const u64 nwords = ix.ntiles * (FQ_TILE_BYTES / 64);
+      const u32 pos0 = ix.cta_pos[blockIdx.x];
+      u64 w = pos0 >> 6;
+      u32 found = 0, buf = 0;
+      u64 keep = ~0ull << (pos0 & 63u);                // first word: newlines before the CTA's first one belong to the previous CTA
+      while (found < need && w < nwords) {             // CTA-uniform
+        const u64 idx = w + tid;
+        u64 mm = idx < nwords ? ix.nlmask64[idx] : 0ull;
+        if (tid == 0) mm &= keep;
+        keep = ~0ull;
+        const u32 cnt = (u32)__popcll(mm);
+        u32 inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += y; }
+        if (lane == 31) s_wsum[buf * V5_WARPS + wid] = inc;
+        __syncthreads();
+        u32 before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < V5_WARPS; i++) { const u32 v = s_wsum[buf * V5_WARPS + i]; if ((u32)i < wid) before += v; total += v; }
+        u32 rank = found + before + inc - cnt;
+        const u32 wbase = (u32)(idx * 64 - ix.lead);
+        while (mm && rank < need) {
+          s_nl[rank++] = wbase + (u32)(__ffsll((long long)mm) - 1);
+          mm &= mm - 1;
+        }
+        found += total;
+        w += V5_THREADS; buf ^= 1u;
+      }
+    }
+    __syncthreads();
+    for (u32 r = tid; r < R; r += V5_THREADS) {
+      u32 len = 0, st = 0;
+      if (r < nr) {
+        const u64 nbytes = ix.tot - ix.lead;
+        const u32 h = s_nl[4 * r], e = s_nl[4 * r + 1], q = s_nl[4 * r + 3];
+        if (h == 0xFFFFFFFFu || e == 0xFFFFFFFFu) bad = 1;
+        else {
+          st = h + 1; len = e - st;
+          // A trailing CR (dropped by kseq when the line is longer than 1, BankFasta.cpp:476-477) is kept as an invalid last
+          // base: the k-mers that would cover it do not exist either way.  Only a read one longer than the geometry looks.
+          if (len == ix.geo_maxlen + 1 && a.text[e - 1] == '\r') len--;
+          vplus = ((u64)e + 1 < nbytes) ? a.text[e + 1] : (u32)'+';
+          vat = (q != 0xFFFFFFFFu && (u64)q + 1 < nbytes) ? a.text[q + 1] : (u32)'@';
+        }
+        if (seg0 + r == 0 && a.text[0] != '@') bad = 1;
+        if (len > ix.geo_maxlen) { atomicOr(&ix.flags[3], 1u); len = 0; }
+        if (bad) len = 0;
+      }
+      if (len < (u32)a.k) len = 0;
+      x.len[r] = len; x.start[r] = st; x.inval[r] = 0;
+    }
   }
   __syncthreads();
 
@@ -50,6 +149,7 @@ s1_superk_v5(const S1Args a, const Geo geo)
       if (c >= geo.nch) { c -= geo.nch; r++; }
     }
   }
+  if (FUSED && tid < nr && (bad || vplus != '+' || vat != '@')) atomicOr(&ix.flags[0], 1u);   // not strict 4-line FASTQ: the host redoes the block
   __syncthreads();
 
   // ---- P1: lut values, one warp per read, lanes over the m-mers
@@ -172,20 +272,30 @@ bool s1_v5_usable(u32 max_len, int k, int m, u32 P, Geo* geo, size_t* smem)
   return true;
 }
 
-cudaError_t launch_s1_v5(int W, const S1Args& a, const Geo& geo, size_t smem, cudaStream_t st, u64* launches)
+cudaError_t launch_s1_v5(int W, const S1Args& a, const Geo& geo, size_t smem, const S1Idx* idx, cudaStream_t st, u64* launches)
 {
   if (a.nseg == 0) return cudaSuccess;
   const unsigned grid = (unsigned)((a.nseg + geo.R - 1) / geo.R);
+  S1Idx ix; memset(&ix, 0, sizeof ix);
+  if (idx) ix = *idx;
   cudaError_t e;
-  if (W == 1) {
-    e = cudaFuncSetAttribute(s1_superk_v5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    s1_superk_v5<1><<<grid, V5_THREADS, smem, st>>>(a, geo);
-  } else {
-    e = cudaFuncSetAttribute(s1_superk_v5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    s1_superk_v5<2><<<grid, V5_THREADS, smem, st>>>(a, geo);
-  }
+#define KMX_V5_LAUNCH(WW, FF)                                                                                              \
+  do {                                                                                                                     \
+    e = cudaFuncSetAttribute(s1_superk_v5<WW, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+    if (e != cudaSuccess) return e;                                                                                        \
+    s1_superk_v5<WW, FF><<<grid, V5_THREADS, smem, st>>>(a, geo, ix);                                                      \
+  } while (0)
+  if (idx) { if (W == 1) KMX_V5_LAUNCH(1, true); else KMX_V5_LAUNCH(2, true); }
+  else { if (W == 1) KMX_V5_LAUNCH(1, false); else KMX_V5_LAUNCH(2, false); }
+#undef KMX_V5_LAUNCH
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fq_cta_pos(const u64* nlmask64, const u64* tile_prefix, u64 ntiles, u32* cta_pos, u64 ncta, cudaStream_t st, u64* launches)
+{
+  if (!ntiles) return cudaSuccess;
+  fq_cta_pos<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(nlmask64, tile_prefix, ntiles, cta_pos, ncta);
   *launches += 1;
   return cudaGetLastError();
 }

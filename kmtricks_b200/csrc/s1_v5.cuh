@@ -21,8 +21,8 @@
 //       (CTA, partition), records built by funnel shifts from the packed forward stream
 //
 // The phase bodies are plain functions of (item index, shared arrays) and compile for the host
-// too: tests/emul/s1v5_emul.cpp runs a CTA phase by phase on the CPU against the oracle, so
-// the index arithmetic is checked without a GPU.
+// too: tests/emul/s1v5_emul.cpp runs a CTA phase by phase on the CPU and checks the emitted records,
+// so the index arithmetic is tested without a GPU.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>

@@ -118,6 +118,73 @@ def test_stage1_position_parallel_reads_per_cta(R, synth_samples, edge_samples, 
         _compare(got, want, CASES["kmer_count"]["P"], len(samples))
 
 
+def _fq(reads, crlf=False, trailing_newline=True):
+    nl = b"\r\n" if crlf else b"\n"
+    t = b"".join(b"@q%d" % i + nl + r + nl + b"+" + nl + b"I" * len(r) + nl for i, r in enumerate(reads))
+    return t if trailing_newline else t[:-len(nl)]
+
+
+def test_stage1_self_indexing_launch(monkeypatch):
+    """After the first FASTQ block of a run, stage 1 finds its reads in the newline masks itself (no line-index
+    pass).  Blocks with CRLF line ends, N / lower case, reads shorter than k, no final newline, many small
+    records (several CTAs per tile) and few long ones (several tiles per CTA) must take that path and give the
+    oracle's bytes; a block with a longer read than seen before falls back to the indexed path; the switch
+    KMX_S1_NOFUSE gives the same bytes."""
+    import random
+    rnd = random.Random(5)
+    genome = "".join(rnd.choice("ACGT") for _ in range(30000))
+
+    def reads(n, lo, hi, noise=0.0):
+        out = []
+        for _ in range(n):
+            L = rnd.randint(lo, hi); p = rnd.randrange(len(genome) - L)
+            r = list(genome[p:p + L])
+            for j in range(L):
+                if rnd.random() < noise:
+                    r[j] = rnd.choice("NnacgtRY")
+            out.append("".join(r).encode())
+        return out
+
+    samples = [
+        [_fq(reads(700, 250, 250))],                                   # sets the length hint (indexed path)
+        [_fq(reads(900, 20, 250, noise=0.01), crlf=True)],             # self-indexed: CRLF, invalid letters, reads < k
+        [_fq(reads(5000, 31, 40)), _fq(reads(300, 200, 250), trailing_newline=False)],
+        [_fq(reads(64, 250, 250) + reads(1, 300, 300) + reads(64, 100, 250))],   # longer read: falls back, raises the hint
+        [_fq(reads(400, 280, 300, noise=0.002), trailing_newline=False)],
+    ]
+    case = dict(k=31, P=8, mode="kmer:count:bin", hard_min=1)
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    assert got["s1_self_indexed"] == 4 and got["s1_indexed"] == 2, (got["s1_self_indexed"], got["s1_indexed"])
+    monkeypatch.setenv("KMX_S1_NOFUSE", "1")
+    got2, _ = _run_both(samples, case)
+    assert got2["s1_self_indexed"] == 0
+    assert got2["matrices"] == got["matrices"] and got2["counts"] == got["counts"]
+
+
+def test_stage1_self_indexing_rejects_malformed_fastq():
+    """A block that is not strict 4-line FASTQ gets the format status on the self-indexing path too (the host
+    then parses it kseq-style), and the sample's buckets are left as they were."""
+    from kmtricks_b200 import engine, _lib
+    good = _fq([b"ACGTTGCA" * 10] * 50)
+    bad = good.replace(b"\n+\n", b"\n-\n", 1)
+    cfg = engine.Config(kmer_size=31, nb_partitions=4, mode="kmer:count:bin", hard_min=1)
+    eng = engine.Engine(cfg, 2)
+    try:
+        L = eng.lib
+        pin1 = eng.superk([good])
+        assert L.kmx_superk_begin(eng.h) == 0
+        assert L.kmx_superk_push_fastq(eng.h, bad, len(bad), 0) == _lib.KMX_ERR_FORMAT
+        assert L.kmx_superk_push_fastq(eng.h, good, len(good), 0) == 0
+        pin2 = np.zeros(4, dtype=np.uint64)
+        import ctypes as C
+        assert L.kmx_superk_end(eng.h, pin2.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+        assert list(pin1) == list(pin2)
+        assert int(L.kmx_stat(eng.h, 0)) == 1
+    finally:
+        eng.close()
+
+
 def test_hash_mode_larger_sample_all_paths(monkeypatch):
     """One sample large enough that every partition spans several histogram tiles and sweep chunks
     (tile tickets wrap over windows, partial last chunk), default and fused kernels."""

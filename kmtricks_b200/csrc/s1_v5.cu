@@ -11,7 +11,7 @@ namespace kmx {
 
 using namespace s1v5;
 
-static constexpr int V5_THREADS = 256;
+static constexpr int V5_THREADS = 320;       // 10 warps: one round of the pack phase for 32 reads of <= 160 bases
 static constexpr int V5_WARPS = V5_THREADS / 32;
 
 // byte position (in the coordinates of the mask array) of newline number 4 * S1_FUSED_R * c, for every CTA c of the
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(V5_THREADS)
 s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
 {
   extern __shared__ __align__(16) u32 smem5[];
-  __shared__ u32 s_end;
+  __shared__ u32 s_nev, s_pend;
   Cta x;
   x.k = a.k; x.m = a.m; x.w = a.wlen; x.max_nk = (u32)a.max_nk;
   x.mmask = (u32)((1ull << (2 * a.m)) - 1ull);
@@ -61,6 +61,8 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
   const u64 seg0 = (u64)blockIdx.x * R;
 
   for (u32 p = tid; p < a.P; p += V5_THREADS) { x.hist[p] = 0; x.kc[p] = 0; }
+  for (u32 t = tid; t < geo.R * geo.nblk; t += V5_THREADS) x.done[t] = 0;
+  if (tid == 0) { s_nev = 0; s_pend = 0; }
   u32 nr = 0, bad = 0, vplus = '+', vat = '@';       // self-indexing launch: format checks, consumed after P0 (their loads overlap it)
   if (!FUSED) {
     for (u32 r = tid; r < R; r += V5_THREADS) {
@@ -165,48 +167,24 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
     for (u32 r = lane; r < R; r += 32) p2_block(x, r, g, x.len[r]);
   __syncthreads();
 
-  // ---- P3a per read, P3b count per item (read, block)
+  // ---- P3 + P4, in rounds (one round unless the CTA logs more events than its queue holds): every pending item
+  // (read, block) completes its change mask, counts its records, takes that many queue slots with ONE shared-memory
+  // atomic, logs its events and (P4 pass 1) looks up their partition, per-partition rank and k-mer totals
   const u32 ntask = R * geo.nblk;
-  for (u32 r = tid; r < R; r += V5_THREADS) p3a_read(x, r, x.len[r]);
-  __syncthreads();
-  for (u32 t = tid; t < ntask; t += V5_THREADS) { const u32 r = item_read(geo, t); x.pfx[t + 1] = p3_count(x, r, t - r * geo.nblk, x.len[r]); }
-  __syncthreads();
-  if (wid == 0) {                                   // counts at pfx[1..ntask] -> inclusive prefix in place (pfx[t] = events before item t)
-    const u32 per = (ntask + 31) / 32;
-    const u32 i0 = min(ntask, lane * per), i1 = min(ntask, i0 + per);
-    u32 sum = 0;
-    for (u32 i = i0; i < i1; i++) sum += x.pfx[i + 1];
-    u32 inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += y; }
-    u32 run = inc - sum;
-    for (u32 i = i0; i < i1; i++) { run += x.pfx[i + 1]; x.pfx[i + 1] = run; }
-    if (lane == 0) x.pfx[0] = 0;
-  }
-  __syncthreads();
-
-  u32 first = 0;
-  while (first < ntask) {
-    // items [first, end) are flushed in this round: the longest prefix whose events fit the queue
-    const u32 base = x.pfx[first];
-    u32 end = ntask;
-    if (x.pfx[ntask] - base > geo.evcap) {          // CTA-uniform; the usual case is one round, no search
-      for (u32 t = first + tid; t < ntask; t += V5_THREADS) {
-        const bool fits = x.pfx[t + 1] - base <= geo.evcap;
-        if (fits && x.pfx[t + 2] - base > geo.evcap) s_end = t + 1;      // exactly one writer (prefix sums are monotone; t + 1 < ntask here)
+  for (;;) {
+    for (u32 t = tid; t < ntask; t += V5_THREADS) {
+      if (x.done[t]) continue;
+      const u32 r = item_read(geo, t), g = t - r * geo.nblk;
+      const u32 n = p3_prepare(x, r, g, x.len[r]);
+      if (!n) { x.done[t] = 1; continue; }
+      const u32 s0 = atomicAdd(&s_nev, n);
+      if (s0 + n > geo.evcap) {                      // does not fit this round: pad what was taken, try again after the flush
+        for (u32 q = s0; q < geo.evcap; q++) { Ev z; z.x = 0; z.y = 0; x.ev[q] = z; }
+        s_pend = 1;
+        continue;
       }
-      if (tid == 0 && x.pfx[first + 1] - base > geo.evcap) s_end = first; // no item fits: cannot happen (evcap >= events of any item)
-      __syncthreads();
-      end = s_end;
-      if (end <= first) { if (tid == 0) *a.overflow = 1u; return; }       // fail loudly through the host's retry limit
-    }
-    const u32 nev = x.pfx[end] - base;
-    // ---- P3c: the events of one item per thread, then (P4 pass 1) their partition, per-partition rank and k-mer totals
-    for (u32 t = first + tid; t < end; t += V5_THREADS) {
-      const u32 s0 = x.pfx[t] - base, n = x.pfx[t + 1] - x.pfx[t];
-      if (!n) continue;
-      const u32 r = item_read(geo, t);
-      if (!x.inval[r]) p3_emit_item(x, r, t - r * geo.nblk, s0);
+      x.done[t] = 1;
+      if (!x.inval[r]) p3_emit_item(x, r, g, s0);
       else p3_slow<true>(x, r, x.len[r], s0);       // reads with invalid bases: per-k-mer walk (all their events sit in block 0's item)
       u32 q = s0;
       for (; q + 2 <= s0 + n; q += 2) {
@@ -225,6 +203,7 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
       }
     }
     __syncthreads();
+    const u32 nev = min(s_nev, geo.evcap), pend = s_pend;
     for (u32 p = tid; p < a.P; p += V5_THREADS) {
       const u32 cnt = x.hist[p];
       if (cnt) {
@@ -240,6 +219,7 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
       const Ev e = x.ev[q];
       const u32 p = e.y & 0xFFFFu;
       const u32 rd = e.x & 127u, iend = (e.x >> 7) & 4095u, nkr = (e.x >> 19) & 127u;
+      if (!nkr) continue;                             // padding of an item that did not fit
       const u32 nb = (u32)a.k + nkr - 1u;
       u32 v[4 * W];
       build_record<4 * W>(x.BE + rd * geo.LW, geo.nch, iend, nb, v);
@@ -251,7 +231,9 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
       } else *a.overflow = 1u;
     }
     __syncthreads();
-    first = end;
+    if (!pend) break;
+    if (tid == 0) { s_nev = 0; s_pend = 0; }
+    __syncthreads();
   }
 }
 

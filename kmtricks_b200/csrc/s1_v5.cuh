@@ -14,9 +14,9 @@
 //       out of the two packed streams, lut value by arithmetic
 //   P2  one block of w = k-m+1 k-mers per item: sliding-window minimum by block suffix /
 //       running prefix minima (van Herk), minimizer-change bitmask of the block
-//   P3  one block of one read per item: walks the set bits of the block's change mask (about one
-//       per 11 k-mers) and logs one event per record (count pass, prefix sum, emit pass); a read
-//       with invalid bases takes a per-k-mer walk by one thread
+//   P3  one block of one read per item: completes the block's change mask, counts its records (about
+//       one per 11 k-mers), takes that many slots of the CTA's event queue with one shared-memory
+//       atomic and logs one event per record; a read with invalid bases takes a per-k-mer walk by one thread
 //   P4  flush (as in s1_superk): per-partition ranking in shared memory, ONE global atomic per
 //       (CTA, partition), records built by funnel shifts from the packed forward stream
 //
@@ -115,7 +115,7 @@ KMX_HD Geo make_geo(u32 R, u32 maxlen, int k, int m)
   g.inv_nblk = g.nblk >= 2 ? (u32)((0x100000000ull + g.nblk - 1) / g.nblk) : 0u;
   return g;
 }
-// 32-bit words of shared memory: BE | LE | CH | U (later the event queue) | S | NX | len | start | inval | pfx | hist | gbase | kc | VB (u16)
+// 32-bit words of shared memory: BE | LE | CH | U (later the event queue) | S | NX | len | start | inval | done | hist | gbase | kc | VB (u16)
 KMX_HD size_t smem_words(const Geo& g, u32 P)
 {
   const size_t nt = (size_t)g.R * g.nblk;
@@ -138,7 +138,7 @@ struct Ev { u32 x, y; };   // x = read | (base index just past the record) << 7 
 struct Cta {
   int k, m, w; u32 max_nk, mmask, ban_mask;
   Geo g;
-  u32 *BE, *LE, *U, *S, *CH, *NX, *len, *start, *inval, *pfx, *hist, *gbase, *kc;
+  u32 *BE, *LE, *U, *S, *CH, *NX, *len, *start, *inval, *done, *hist, *gbase, *kc;
   uint16_t* VB;
   Ev* ev;
 };
@@ -154,7 +154,7 @@ KMX_HD void carve(Cta& x, u32* base /* 8-byte aligned */, u32 P)
   x.S = p; p += (size_t)g.R * g.Spad;
   x.NX = p; p += nt;
   x.len = p; p += g.R; x.start = p; p += g.R; x.inval = p; p += g.R;
-  x.pfx = p; p += nt + 1;
+  x.done = p; p += nt + 1;
   x.hist = p; p += P; x.gbase = p; p += P; x.kc = p; p += P;
   x.VB = reinterpret_cast<uint16_t*>(p);
 }
@@ -328,26 +328,35 @@ KMX_HD void p2_block(const Cta& x, u32 r, u32 g, u32 len)
 }
 
 // ---- P3 -------------------------------------------------------------------------------------
-// P3a, one read per item: bit 0 of every block's change mask (needs the neighbour block's last
-// minimizer), then NX[g] = first cut after block g (or nk), found walking the blocks backwards
-KMX_HD void p3a_read(const Cta& x, u32 r, u32 len)
+// P3a, item (r, g): completes the block's change mask (bit 0 needs the neighbour block's last minimizer),
+// finds NX = the first cut after the block (looking ahead over blocks without a cut) and returns the number
+// of records that START in the block.  Every run but the last one of the block ends inside the block
+// (shorter than w <= max_nk: one record each); the last one runs to NX.
+KMX_HD u32 p3_slow_count(const Cta& x, u32 r, u32 len);
+KMX_HD u32 p3_prepare(const Cta& x, u32 r, u32 g, u32 len)
 {
   const u32 k = (u32)x.k, w = (u32)x.w;
-  if (len < k) return;
-  const u32 nk = len - k + 1u;
+  if (len < k) return 0;
+  const u32 nk = len - k + 1u, lo = g * w;
+  if (lo >= nk) return 0;
+  if (x.inval[r]) return g == 0 ? p3_slow_count(x, r, len) : 0u;
   const u32* M = x.S + r * x.g.Spad;
-  u32* ch = x.CH + 2 * r * x.g.nblk;
-  u32* nx = x.NX + r * x.g.nblk;
-  const u32 nb = (nk + w - 1) / w;
-  u32 run = nk;
-  for (u32 g = nb; g-- > 0;) {
-    const u32 lo = g * w;
-    u32 c0 = ch[2 * g];
-    if (g == 0 || M[lo] != M[lo - 1]) { c0 |= 1u; ch[2 * g] = c0; }
-    nx[g] = run;
-    const u64 mask = (u64)c0 | ((u64)ch[2 * g + 1] << 32);
-    if (mask) run = lo + ctz64(mask);
+  u32* ch = x.CH + 2 * (r * x.g.nblk + g);
+  u32 c0 = ch[0];
+  if (g == 0 || M[lo] != M[lo - 1]) { c0 |= 1u; ch[0] = c0; }
+  const u64 mask = (u64)c0 | ((u64)ch[1] << 32);
+  if (!mask) return 0;
+  u32 nxt = nk;
+  for (u32 g2 = g + 1, lo2 = lo + w; lo2 < nk; g2++, lo2 += w) {
+    // the owner of block g2 may or may not have set its bit 0 yet: recompute it
+    const u64 m2 = (u64)(ch[2 * (g2 - g)] | (u32)(M[lo2] != M[lo2 - 1])) | ((u64)ch[2 * (g2 - g) + 1] << 32);
+    if (m2) { nxt = lo2 + ctz64(m2); break; }
   }
+  x.NX[r * x.g.nblk + g] = nxt;
+  u32 last = nxt - (lo + 63u - clz64(mask));            // k-mers in the last run
+  u32 n = popc64(mask);
+  while (last > x.max_nk) { last -= x.max_nk; n++; }
+  return n;
 }
 
 // events of the run of k-mers [a, b) with one minimizer: pieces of at most max_nk k-mers.
@@ -387,23 +396,8 @@ KMX_HD u32 p3_slow(const Cta& x, u32 r, u32 len, u32 slot)
   if (open) n += p3_run<EMIT>(x, r, M, s0, s0 + nn, slot + n);
   return n;
 }
-// P3b, item (r, g): number of records that START in block g.  Every run but the last one of the block
-// ends inside the block (shorter than w <= max_nk: one record each); the last one runs to NX[g]
-KMX_HD u32 p3_count(const Cta& x, u32 r, u32 g, u32 len)
-{
-  const u32 k = (u32)x.k, w = (u32)x.w;
-  if (len < k) return 0;
-  const u32 nk = len - k + 1u, lo = g * w;
-  if (lo >= nk) return 0;
-  if (x.inval[r]) return g == 0 ? p3_slow<false>(x, r, len, 0) : 0u;
-  const u32* ch = x.CH + 2 * (r * x.g.nblk + g);
-  const u64 mask = (u64)ch[0] | ((u64)ch[1] << 32);
-  if (!mask) return 0;
-  u32 last = x.NX[r * x.g.nblk + g] - (lo + 63u - clz64(mask));     // k-mers in the last run
-  u32 n = popc64(mask);
-  while (last > x.max_nk) { last -= x.max_nk; n++; }
-  return n;
-}
+KMX_HD u32 p3_slow_count(const Cta& x, u32 r, u32 len) { return p3_slow<false>(x, r, len, 0); }
+
 // P3c, item (r, g): its events -> x.ev[slot ...] in k-mer order, y = minimizer.  (Reads with invalid
 // bases are emitted by p3_slow<true>, one thread per read.)
 KMX_HD void p3_put(const Cta& x, u32 slot, u32 r, u32 s, u32 e, u32 mz)

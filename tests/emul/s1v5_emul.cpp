@@ -130,37 +130,38 @@ int main(int argc, char** argv)
     for (uint32_t r = 0; r < R; r++) { uint32_t len = x.len[r]; if (!len) continue; for (uint32_t lane = 0; lane < 32; lane++) p1_row(x, r, lane, len - m + 1); }
     // P2
     for (uint32_t g = 0; g < x.g.nblk; g++) for (uint32_t r = 0; r < R; r++) p2_block(x, r, g, x.len[r]);
-    // P3a per read, P3b count per item, prefix, rounds of P3c emit (one event per work item), P4
-    for (uint32_t r = 0; r < R; r++) p3a_read(x, r, x.len[r]);
+    // P3 rounds: every pending item (r, g) prepares (mask bit 0, look-ahead, count), takes its slots with an atomic add on the
+    // CTA's event counter and emits if they fit the queue; otherwise it pads what it took and waits for the next round. P4 follows.
     const uint32_t ntask = R * x.g.nblk;                       // item = r * nblk + g
-    std::vector<uint32_t> cnt(ntask);
-    for (uint32_t t = 0; t < ntask; t++) cnt[t] = x.pfx[t + 1] = p3_count(x, t / x.g.nblk, t % x.g.nblk, x.len[t / x.g.nblk]);
-    x.pfx[0] = 0;
-    for (uint32_t t = 0; t < ntask; t++) x.pfx[t + 1] += x.pfx[t];
-    uint32_t first = 0;
-    while (first < ntask) {
-      const uint32_t base = x.pfx[first];
-      uint32_t end = first;
-      for (uint32_t t = first; t < ntask; t++) if (x.pfx[t + 1] - base <= x.g.evcap) end = std::max(end, t + 1);
-      if (end == first) { fprintf(stderr, "item with %u events does not fit\n", cnt[first]); return 1; }
-      const uint32_t acc = x.pfx[end] - base;
-      for (uint32_t q = 0; q < acc; q++) { x.ev[q].x = 0xFFFFFFFFu; x.ev[q].y = 0xFFFFFFFFu; }
-      for (uint32_t t = first; t < end; t++) {                  // as the kernel: one item per thread
+    std::vector<uint32_t> cnt(ntask, 0);
+    for (uint32_t t = 0; t < ntask; t++) x.done[t] = 0;
+    uint32_t pending = ntask;
+    while (pending) {
+      uint32_t s_nev = 0, progressed = 0;
+      for (uint32_t t = 0; t < ntask; t++) {
+        if (x.done[t]) continue;
         const uint32_t r = item_read(x.g, t);
         if (r != t / x.g.nblk) { fprintf(stderr, "item_read(%u) = %u\n", t, r); return 1; }
-        if (!cnt[t] || x.inval[r]) continue;
-        p3_emit_item(x, r, t % x.g.nblk, x.pfx[t] - base);
-      }
-      for (uint32_t r = 0; r < R; r++) {
-        const uint32_t t = r * x.g.nblk;
-        if (x.inval[r] && x.len[r] && t >= first && t < end) {
-          uint32_t n = p3_slow<true>(x, r, x.len[r], x.pfx[t] - base);
-          if (n != cnt[t]) { fprintf(stderr, "count/emit mismatch read %u: %u vs %u\n", r, n, cnt[t]); return 1; }
+        const uint32_t g = t % x.g.nblk;
+        const uint32_t n = p3_prepare(x, r, g, x.len[r]);
+        cnt[t] = n;
+        const uint32_t s0 = s_nev; s_nev += n;                  // atomicAdd
+        if (s0 + n <= x.g.evcap) {
+          if (n) {
+            if (!x.inval[r]) p3_emit_item(x, r, g, s0);
+            else if (p3_slow<true>(x, r, x.len[r], s0) != n) { fprintf(stderr, "count/emit mismatch read %u\n", r); return 1; }
+          }
+          x.done[t] = 1; pending--; progressed++;
+        } else {
+          for (uint32_t q = s0; q < x.g.evcap; q++) { x.ev[q].x = 0; x.ev[q].y = 0; }   // null events: skipped by the flush
         }
       }
+      if (!progressed) { fprintf(stderr, "no item fits the event queue\n"); return 1; }
+      const uint32_t acc = std::min(s_nev, x.g.evcap);
       nev_rounds++;
       for (uint32_t q = 0; q < acc; q++) {
         const Ev e = x.ev[q];
+        if (!(e.x >> 19)) continue;                              // padding of an item that did not fit
         const uint32_t rd = e.x & 127u, iend = (e.x >> 7) & 4095u, nkr = (e.x >> 19) & 127u;
         if (e.y > x.mmask) { fprintf(stderr, "minimizer out of range\n"); return 1; }
         const uint32_t p = table[e.y];
@@ -182,7 +183,6 @@ int main(int argc, char** argv)
         for (uint32_t j = 0; j < nkr; j++) { uint64_t lo, hi; canon_of(codes.data() + j, k, lo, hi); got.emplace_back(p, hi, lo); }
         kcnt[p] += nkr; cursor[p]++; nrec++; if (nkr == max_nk) nfull++;
       }
-      first = end;
     }
   }
   std::sort(want.begin(), want.end()); std::sort(got.begin(), got.end());

@@ -437,6 +437,14 @@ def main_kmx(args):
             alg_s2 = BUCKET_BYTES_PER_KMER * kmers_step + (key_b + 4) * D / max(world, 1)
             alg_s34 = (key_b + 4) * D + body_sum[0] * (2 if fmt == "bft" else 1)
             alg_all = alg_s1 + alg_s2 + alg_s34
+            # every timed span against the same roofline (algorithmic bytes of its stage per step / its CUDA-event time per step)
+            span_alg = {"fq_index": N * sample_bytes, "s1_superk": alg_s1, "hash_hist": BUCKET_BYTES_PER_KMER * kmers_step,
+                        "hash_emit": (key_b + 4) * D / max(world, 1), "expand": BUCKET_BYTES_PER_KMER * kmers_step,
+                        "radix_sort": (key_b + 4) * D / max(world, 1), "rle": (key_b + 4) * D / max(world, 1), "merge": alg_s34}
+            roof["per_span"] = {k: {"ms_per_step": round(v["ms_per_step"], 3), "algorithmic_bytes_per_step": span_alg[k],
+                                    "achieved": span_alg[k] / (v["ms_per_step"] * 1e-3) / 1e9,
+                                    "frac": span_alg[k] / (v["ms_per_step"] * 1e-3) / 1e9 / peak}
+                                for k, v in prof.items() if k in span_alg and v["ms_per_step"] > 0}
             roof["pipeline"] = {"algorithmic_bytes_per_step": alg_all, "achieved": alg_all / (ms_step * 1e-3) / 1e9,
                                 "frac": alg_all / (ms_step * 1e-3) / 1e9 / peak, "surviving_key_sample_pairs": D,
                                 "what": "S1 text+buckets, S2 buckets+lists, S3/S4 lists+bodies (SURVEY 8d) over ms_per_step"}

@@ -17,7 +17,7 @@ OUT = sys.argv[2] if len(sys.argv) > 2 else "r01c"
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-SPAN = {"fq_count_newlines": "fq_index", "scan_u32_to_u64": "fq_index", "fq_index_lines": "fq_index", "s1_superk": "s1_superk",
+SPAN = {"fq_count_newlines": "fq_index", "scan_u32_to_u64": "fq_index", "fq_index_lines": "fq_index", "fq_cta_pos": "fq_index", "s1_superk": "s1_superk", "s1_superk_v5": "s1_superk",
         "hash_hist_roll_kernel": "hash_hist", "hash_hist_kernel": "hash_hist", "hash_compact_kernel": "hash_emit",
         "hash_scan_kernel": "hash_emit", "hash_copy_kernel": "hash_emit", "merge_emit_kernel": "merge", "merge_solid_kernel": "merge"}
 
@@ -79,7 +79,7 @@ seen = set()
 with open(os.path.join(P, f"{OUT}_ncu_full_summary.md"), "w") as f:
     f.write("# Round 1 (final state) -- ncu --set full, hot-path kernels of ONE sample launch (1M reads x 150 nt, 1.2e8 k-mers, k=31, hash keys, P=64, bloom 2e8)\n\n")
     f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:\"s1_superk|hash_hist_roll|hash_compact|hash_copy|hash_scan|"
-            "fq_index_lines|fq_count_newlines\" -s 7 -c 7 -o gpurun_out/prof_%s python bench.py --samples 2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --lanes 1`\n\n" % T)
+            "fq_index_lines|fq_count_newlines|fq_cta_pos\" -s 7 -c 7 -o gpurun_out/prof_%s python bench.py --samples 2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --lanes 1`\n\n" % T)
     f.write("| kernel | " + " | ".join(w.replace(".avg.pct_of_peak_sustained", ".pct") for w in want) + " |\n|" + "---|" * (len(want) + 1) + "\n")
     # ncu reports a per-row unit in the metric-unit row only; values with mixed units are normalised below
     for r in rows[2:]:

@@ -237,9 +237,9 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
   }
 }
 
-// can this launch take the position-parallel kernel?  (events of one read must fit a flush round,
+// can this launch take the position-parallel kernel?  (the events of one read must fit the event queue,
 // the event word holds 7 bits of read index and 12 bits of base index, the arrays must leave room
-// for >= 2 CTAs per SM)
+// for >= 2 CTAs per SM, and a block of w k-mers must fit one record: p3_prepare's closed-form count)
 bool s1_v5_usable(u32 max_len, int k, int m, u32 P, Geo* geo, size_t* smem)
 {
   const bool off = kmx_env_flag("KMX_S1V5_OFF");
@@ -249,7 +249,7 @@ bool s1_v5_usable(u32 max_len, int k, int m, u32 P, Geo* geo, size_t* smem)
   Geo g = make_geo(R, max_len, k, m);
   const size_t b = smem_bytes(g, P);
   const int max_nk = (k <= 32 ? KMX_REC1_MAXN : KMX_REC2_MAXN) - k + 1;
-  if (b > 100 * 1024 || max_len - (u32)k + 1u > g.evcap || k - m + 1 > max_nk) return false;   // p3_count: a block's inner runs are single records
+  if (b > 100 * 1024 || max_len - (u32)k + 1u > g.evcap || k - m + 1 > max_nk) return false;
   *geo = g; *smem = b;
   return true;
 }

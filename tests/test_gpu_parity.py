@@ -118,6 +118,29 @@ def test_stage1_position_parallel_reads_per_cta(R, synth_samples, edge_samples, 
         _compare(got, want, CASES["kmer_count"]["P"], len(samples))
 
 
+def test_long_sequences_take_the_streaming_kernel():
+    """Contigs / long reads (FASTA, multi-line, with N runs; FASTQ reads of 400-900 nt): longer than the shared arrays of
+    the position-parallel kernel, so stage 1 streams them (sequences beyond 1054 nt are cut into overlapping segments
+    by the host side of kmx_superk_push_reads)."""
+    import random
+    rnd = random.Random(11)
+
+    def seq(n):
+        s = [rnd.choice("ACGT") for _ in range(n)]
+        for _ in range(n // 3000):
+            p = rnd.randrange(n - 40); s[p:p + rnd.randint(1, 35)] = "N" * rnd.randint(1, 35)
+        return "".join(s)
+
+    contigs = [seq(n) for n in (12345, 5000, 1054, 1055, 2048, 2049, 31, 30, 3000)]
+    fasta = "".join(">c%d\n%s\n" % (i, "\n".join(c[j:j + 70] for j in range(0, len(c), 70))) for i, c in enumerate(contigs)).encode()
+    long_reads = [seq(rnd.randint(400, 900)).encode() for _ in range(60)]
+    fastq = b"".join(b"@l%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(long_reads))
+    samples = [[fasta], [fastq, fasta[:20000] + b"\n"], [fastq]]
+    for name in ("kmer_count", "k63_kmer_pa", "hash_bf"):
+        got, want = _run_both(samples, CASES[name])
+        _compare(got, want, CASES[name]["P"], len(samples))
+
+
 def _fq(reads, crlf=False, trailing_newline=True):
     nl = b"\r\n" if crlf else b"\n"
     t = b"".join(b"@q%d" % i + nl + r + nl + b"+" + nl + b"I" * len(r) + nl for i, r in enumerate(reads))

@@ -45,7 +45,7 @@ fq_cta_pos(const u64* __restrict__ nlmask64, const u64* __restrict__ tile_prefix
 }
 
 template <int W, bool FUSED>
-__global__ void __launch_bounds__(V5_THREADS)
+__global__ void __launch_bounds__(V5_THREADS, 5)
 s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
 {
   extern __shared__ __align__(16) u32 smem5[];
@@ -163,8 +163,13 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
   __syncthreads();
 
   // ---- P2: sliding minimum, lane = read (odd row pitch: conflict-free), warp = block
-  for (u32 g = wid; g < geo.nblk; g += V5_WARPS)
-    for (u32 r = lane; r < R; r += 32) p2_block(x, r, g, x.len[r]);
+  if (a.wlen == 22) {                                // the default k = 31, m = 10: straight-line code
+    for (u32 g = wid; g < geo.nblk; g += V5_WARPS)
+      for (u32 r = lane; r < R; r += 32) p2_block<22>(x, r, g, x.len[r]);
+  } else {
+    for (u32 g = wid; g < geo.nblk; g += V5_WARPS)
+      for (u32 r = lane; r < R; r += 32) p2_block<0>(x, r, g, x.len[r]);
+  }
   __syncthreads();
 
   // ---- P3 + P4, in rounds (one round unless the CTA logs more events than its queue holds): every pending item

@@ -233,8 +233,8 @@ KMX_HD void p1_row(const Cta& x, u32 r, u32 lane, u32 nm)
     const u32 fm = fsl(b1w, b0w, q2) >> sh;       /* bases a .. a+m-1, first base most significant */   \
     const u32 rm = fsr(l0w, l1w, q2) & mmask;     /* its reverse complement */                          \
     const u32 canon = umin(fm, rm);                                                                     \
-    u32 t = ~(canon | (canon >> 2));                                                                    \
-    t = ((t >> 1) & t) & ban;                     /* "AA" anywhere but at the two leading bases (Model.hpp:1220-1251) */ \
+    const u32 o2 = canon | (canon >> 2);          /* bit 2j (and 2j+1) clear <=> bases j and j+1 are both A ... */       \
+    const u32 t = ~(o2 | (o2 >> 1)) & ban;        /* ... "AA" anywhere but at the two leading bases (Model.hpp:1220-1251) */ \
     u[32 * (I)] = t ? mmask : canon;                                                                    \
   }
 #ifdef __CUDA_ARCH__
@@ -250,10 +250,12 @@ KMX_HD void p1_row(const Cta& x, u32 r, u32 lane, u32 nm)
 
 // ---- P2: block g of read r: minimizers of k-mers [g w, g w + w) and their change mask ----
 // window of k-mer t = U[t .. t+w-1] = suffix of block g from t, then prefix of block g+1 up to t+w-1.
-// Loads go in batches of 8 ahead of the serial min chain.
+// Loads go in batches of 8 ahead of the serial min chain.  WC > 0: w is the compile-time constant WC (the default
+// k = 31, m = 10 gives 22) and a full block is one straight line of code with constant offsets; WC = 0: any w.
+template <int WC>
 KMX_HD void p2_block(const Cta& x, u32 r, u32 g, u32 len)
 {
-  const u32 w = (u32)x.w;
+  const u32 w = WC ? (u32)WC : (u32)x.w;
   const u32 nk = len >= (u32)x.k ? len - (u32)x.k + 1u : 0u;
   const u32 lo = g * w;
   u32* ch = x.CH + 2 * (r * x.g.nblk + g);
@@ -261,6 +263,49 @@ KMX_HD void p2_block(const Cta& x, u32 r, u32 g, u32 len)
   const u32* U = x.U + r * x.g.Lpad;
   u32* S = x.S + r * x.g.Spad;
   const u32 hi = lo + w;                              // k-mer lo exists, so m-mers lo .. lo+w-1 do
+  if (WC > 0 && hi <= nk) {                           // all w k-mers of the block exist
+    constexpr int WW = WC > 0 ? WC : 1;
+    const u32* Ub = U + lo; u32* Sb = S + lo;
+    u32 acc = INF;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int b = (WW - 1) / 8; b >= 0; b--) {         // suffix minima, batches [8b, 8b+8) from the top
+      u32 v[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 0; q < 8; q++) if (8 * b + q < WW) v[q] = Ub[8 * b + q];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 7; q >= 0; q--) if (8 * b + q < WW) { acc = umin(acc, v[q]); Sb[8 * b + q] = acc; }
+    }
+    u32 prev = acc, pre = INF, clo = 0, chi = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int b = 0; 4 * b + 1 < WW; b++) {            // k-mers lo + j, j = 1 + 4b + q: window = suffix from j, prefix of the next block up to j + w - 1
+      u32 uu[4], ss[4];                               // (batches of 4: the kernel must stay within 32 registers for 5 CTAs per SM)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; q++) if (1 + 4 * b + q < WW) { uu[q] = Ub[WW + 4 * b + q]; ss[q] = Sb[1 + 4 * b + q]; }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; q++) if (1 + 4 * b + q < WW) {
+        const int j = 1 + 4 * b + q;
+        pre = umin(pre, uu[q]);
+        const u32 mz = umin(ss[q], pre);
+        Sb[j] = mz;
+        if (mz != prev) { if (j < 32) clo |= 1u << (j & 31); else chi |= 1u << (j & 31); }
+        prev = mz;
+      }
+    }
+    ch[0] = clo; ch[1] = chi;
+    return;
+  }
   u32 acc = INF;
   {
     const u32* up = U + hi; u32* sp = S + hi;

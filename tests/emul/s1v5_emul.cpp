@@ -129,7 +129,7 @@ int main(int argc, char** argv)
     // P1
     for (uint32_t r = 0; r < R; r++) { uint32_t len = x.len[r]; if (!len) continue; for (uint32_t lane = 0; lane < 32; lane++) p1_row(x, r, lane, len - m + 1); }
     // P2
-    for (uint32_t g = 0; g < x.g.nblk; g++) for (uint32_t r = 0; r < R; r++) p2_block(x, r, g, x.len[r]);
+    for (uint32_t g = 0; g < x.g.nblk; g++) for (uint32_t r = 0; r < R; r++) { if (x.w == 22) p2_block<22>(x, r, g, x.len[r]); else p2_block<0>(x, r, g, x.len[r]); }
     // P3 rounds: every pending item (r, g) prepares (mask bit 0, look-ahead, count), takes its slots with an atomic add on the
     // CTA's event counter and emits if they fit the queue; otherwise it pads what it took and waits for the next round. P4 follows.
     const uint32_t ntask = R * x.g.nblk;                       // item = r * nblk + g

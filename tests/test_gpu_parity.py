@@ -141,9 +141,9 @@ def test_long_sequences_take_the_streaming_kernel():
         _compare(got, want, CASES[name]["P"], len(samples))
 
 
-def _fq(reads, crlf=False, trailing_newline=True):
+def _fq(reads, crlf=False, trailing_newline=True, comment=b""):
     nl = b"\r\n" if crlf else b"\n"
-    t = b"".join(b"@q%d" % i + nl + r + nl + b"+" + nl + b"I" * len(r) + nl for i, r in enumerate(reads))
+    t = b"".join(b"@q%d" % i + comment + nl + r + nl + b"+" + nl + b"I" * len(r) + nl for i, r in enumerate(reads))
     return t if trailing_newline else t[:-len(nl)]
 
 
@@ -174,11 +174,13 @@ def test_stage1_self_indexing_launch(monkeypatch):
         [_fq(reads(5000, 31, 40)), _fq(reads(300, 200, 250), trailing_newline=False)],
         [_fq(reads(64, 250, 250) + reads(1, 300, 300) + reads(64, 100, 250))],   # longer read: falls back, raises the hint
         [_fq(reads(400, 280, 300, noise=0.002), trailing_newline=False)],
+        [_fq(reads(40, 310, 310))],                                     # longer again: indexed, hint 310 (about the longest the kernel's shared arrays take)
+        [_fq(reads(333, 290, 310, noise=0.001), crlf=True, comment=b" " + b"x" * 90)],   # 32 records > 20 KiB: two windows of mask words per CTA
     ]
     case = dict(k=31, P=8, mode="kmer:count:bin", hard_min=1)
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], len(samples))
-    assert got["s1_self_indexed"] == 4 and got["s1_indexed"] == 2, (got["s1_self_indexed"], got["s1_indexed"])
+    assert got["s1_self_indexed"] == 5 and got["s1_indexed"] == 3, (got["s1_self_indexed"], got["s1_indexed"])
     monkeypatch.setenv("KMX_S1_NOFUSE", "1")
     got2, _ = _run_both(samples, case)
     assert got2["s1_self_indexed"] == 0

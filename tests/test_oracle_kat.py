@@ -82,6 +82,17 @@ def _fixture_table():
     return table
 
 
+def test_repartition_kat_from_repartition_test():
+    """tests/repartition_test.cpp:7-18: four 31-mers whose minimizer (m = 10) falls in partitions 0, 1, 2, 3 of the
+    fixture table tests/data/repart_gatb/repartition.minimRepart."""
+    table = _fixture_table()
+    kmers = ["AATATACTATATAATATATATAGCGAGGGGG", "AAAACGACGACCGCAACACGACGCCAGCAGA",
+             "AAGATATAATATATAAAATATATAGTGTCGT", "AAAAAAAAAAAAAAAAAAAACGCGGCGAAAA"]
+    for want, km in enumerate(kmers):
+        part, lo, hi = O.s1_sequences([km.encode()], 31, 10, table)
+        assert list(part) == [want]
+
+
 def test_stage1_partition_totals_from_task_main():
     """tests/task_main.cpp:59-116: k-mers per partition with the fixture repartition table."""
     table = _fixture_table()

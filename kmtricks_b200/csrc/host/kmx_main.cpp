@@ -238,6 +238,14 @@ int main(int argc, char** argv)
   const auto t0 = std::chrono::steady_clock::now();
   kmx_ctx* ctx = nullptr;
   try {
+    if (argc == 3 && std::string(argv[1]) == "fof") {     // host-side check, no device: prints the parsed input list
+      for (const Sample& s : read_fof(argv[2])) {
+        std::cout << s.id << "\t" << s.hard_min << "\t";
+        for (size_t i = 0; i < s.files.size(); i++) std::cout << (i ? ";" : "") << s.files[i];
+        std::cout << "\n";
+      }
+      return EXIT_SUCCESS;
+    }
     Options o = parse(argc, argv);
     std::vector<Sample> samples = read_fof(o.fof);
     const uint32_t N = (uint32_t)samples.size(), P = o.P, w = (o.k + 31) / 32;

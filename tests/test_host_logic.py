@@ -48,3 +48,26 @@ def test_synth_is_deterministic_and_well_formed():
     lines = a.split(b"\n")
     assert len(lines) == 401 and lines[0] == b"@r00000000" and lines[2] == b"+" and set(lines[1]) <= set(b"ACGT")
     assert len(a) == 100 * synth.record_bytes(80)
+
+
+def test_cli_fof_parser_kat_from_fof_test(tmp_path):
+    """tests/io/fof_test.cpp: the reference's input-list fixture (tests/data/fof.txt, grammar `ID : f1 ; f2 ! hard-min`,
+    include/kmtricks/io/fof.hpp:39-40,115-147) through the C++ host's parser (`kmx fof <file>`, no device needed);
+    duplicate identifiers and lines without ':' are errors as in the reference."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    kmx = os.path.join(root, "kmtricks_b200", "bin", "kmx")
+    if not os.path.exists(kmx):
+        subprocess.run(["bash", os.path.join(root, "build.sh")], check=True)
+    f = tmp_path / "fof.txt"
+    f.write_text("D1 : /path/to/D1.fasta ; /path/to/D1.fasta ! 20\nD2 : /path/to/D2.fasta ; /path/to/D2.fasta ! 20\n")
+    out = subprocess.run([kmx, "fof", str(f)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out == ["D1\t20\t/path/to/D1.fasta;/path/to/D1.fasta", "D2\t20\t/path/to/D2.fasta;/path/to/D2.fasta"]
+    f.write_text("A: x.fa\n\n  B :y.fq.gz;z.fq   \nC : w.fa ! 3\n")
+    out = subprocess.run([kmx, "fof", str(f)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out == ["A\t0\tx.fa", "B\t0\ty.fq.gz;z.fq", "C\t3\tw.fa"]
+    for bad in ("A : x.fa\nA : y.fa\n", "no colon here\n", "A : \n"):
+        f.write_text(bad)
+        r = subprocess.run([kmx, "fof", str(f)], capture_output=True, text=True)
+        assert r.returncode != 0 and r.stderr.strip()

@@ -82,6 +82,19 @@ def _fixture_table():
     return table
 
 
+def test_canonical_kat_from_kmer_test():
+    """tests/kmer_test.cpp:70-82: canonical(AAAAAAACCCCCCC) is itself, canonical(CGCCCCCCCCCCCT) = AGGGGGGGGGGGCG
+    (k-mers compare as integers with A < C < T < G, first base most significant)."""
+    t = O.repart_static(10, 4)
+
+    def dec(v, k):
+        return "".join("ACTG"[(int(v) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+    for seq, want in (("AAAAAAACCCCCCC", "AAAAAAACCCCCCC"), ("CGCCCCCCCCCCCT", "AGGGGGGGGGGGCG")):
+        part, lo, hi = O.s1_sequences([seq.encode()], 14, 10, t)
+        assert dec(lo[0], 14) == want
+
+
 def test_repartition_kat_from_repartition_test():
     """tests/repartition_test.cpp:7-18: four 31-mers whose minimizer (m = 10) falls in partitions 0, 1, 2, 3 of the
     fixture table tests/data/repart_gatb/repartition.minimRepart."""

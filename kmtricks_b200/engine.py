@@ -243,3 +243,32 @@ def run_pipeline(samples: list[list[bytes]], cfg: Config, sample_hard_min: dict 
     finally:
         eng.close()
     return out
+
+
+def run_pipeline_lanes(texts: list[bytes], cfg: Config, lanes: int = 4, device: int = 0, want_counts: bool = True):
+    """Same outputs as run_pipeline, but through kmx_run_samples (several samples in flight on their own
+    streams: the path bench.py times).  One strict 4-line FASTQ text per sample, host buffers."""
+    N = len(texts)
+    eng = Engine(cfg, N, device)
+    L = eng.lib
+    out = dict(pinfo=[], counts={}, matrices={}, merge_info={})
+    try:
+        bufs = [C.create_string_buffer(t, len(t)) for t in texts]
+        ptrs = (C.c_void_p * N)(*[C.addressof(b) for b in bufs])
+        sizes = (C.c_size_t * N)(*[len(t) for t in texts])
+        hm = (C.c_uint32 * N)(*([cfg.hard_min] * N))
+        pin = np.zeros((N, cfg.nb_partitions), dtype=np.uint64)
+        eng._ck(L.kmx_run_samples(eng.h, N, ptrs, sizes, 0, None, hm, lanes, pin.ctypes.data_as(C.POINTER(C.c_uint64))), "run_samples")
+        out["pinfo"] = [pin[s] for s in range(N)]
+        if want_counts:
+            for s in range(N):
+                for p in range(cfg.nb_partitions):
+                    out["counts"][(s, p)] = eng.counts_file(s, p)
+        for p in range(cfg.nb_partitions):
+            m = eng.merge(p)
+            out["matrices"][p] = eng.matrix_file(p, m)
+            out["merge_info"][p] = formats.merge_info(m["stats"])
+        out["launches"] = eng.launches()
+    finally:
+        eng.close()
+    return out

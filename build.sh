@@ -8,7 +8,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall ${KMX_NVCC_EXTRA:-}"
 mkdir -p kmtricks_b200/_build
 pids=()
-for f in s1_superk s1_v5 s2_hash s2_sort s2_ht s3_merge s4_bits synth kmx_api; do
+for f in s1_superk s1_v5 s2_hash s2_bin s2_sort s2_ht s3_merge s4_bits synth kmx_api; do
   [ -f $SRC/$f.cu ] || continue
   if [ ! -f kmtricks_b200/_build/$f.o ] || [ -n "$(find $SRC include -newer kmtricks_b200/_build/$f.o -type f | head -1)" ]; then
     $NVCC $FLAGS -c $SRC/$f.cu -o kmtricks_b200/_build/$f.o &

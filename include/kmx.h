@@ -178,8 +178,10 @@ int kmx_reset(kmx_ctx* ctx);
 /* bytes of device memory currently held by the context */
 uint64_t kmx_device_bytes(const kmx_ctx* ctx);
 /* path counters (tests, bench): FASTQ blocks whose stage 1 found its reads in the newline masks itself
- * (no line-index pass) / blocks that went through the line index */
-enum { KMX_STAT_S1_SELF_INDEXED = 0, KMX_STAT_S1_INDEXED = 1, KMX_STAT_KINDS = 2 };
+ * (no line-index pass) / blocks that went through the line index / hash-count passes on the binned path */
+enum { KMX_STAT_S1_SELF_INDEXED = 0, KMX_STAT_S1_INDEXED = 1,
+       KMX_STAT_HASH_BINNED = 2,   /* samples counted by the binned shared-memory path (hash keys, k <= 32) */
+       KMX_STAT_KINDS = 3 };
 uint64_t kmx_stat(const kmx_ctx* ctx, int which);
 
 #ifdef __cplusplus

@@ -89,6 +89,7 @@ struct Lane {
   char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
   DBuf hist, sub_counts, sub_off, bitmap;
+  DBuf binbuf, binmeta;            // binned hash counting: 16-bit slot offsets per (window, bin) + cursors / look-back words / layout
   u64 d_est = 0;                   // expected surviving (key,count) pairs per sample (grows with what was seen)
   DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt, ht_keys, ht_cnts;
   // ---- profiling
@@ -106,7 +107,8 @@ struct kmx_ctx {
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
-  bool hist16 = true;              // hash histogram with 16-bit counters until one wraps (count_hash_hist)
+  bool hist16 = true;              // hash histogram with 16-bit counters until one wraps (count_hash_hist / count_hash_binned)
+  double bin_slack = 1.25;         // bin-region capacity over the mean bin load (doubles when a bin overflowed; > 8: L2-histogram path)
   int active_lanes = 1;            // lanes running concurrently (sizes the L2-resident histogram groups)
   std::atomic<u64> stat[KMX_STAT_KINDS];
   u32 s1_len_hint = 0;             // longest FASTQ read seen so far: geometry of the self-indexing stage-1 launch (0 = none yet)
@@ -244,7 +246,7 @@ static void lane_destroy(Lane* ln)
 {
   kmx_ctx* ctx = ln->ctx;
   if (ln->st) cudaStreamSynchronize(ln->st);
-  DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->nlmask, &ln->records, &ln->hist,
+  DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->nlmask, &ln->records, &ln->hist, &ln->binbuf, &ln->binmeta,
                   &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->cta_tile, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
@@ -673,11 +675,116 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
   return fail(ln, KMX_ERR_CUDA, "hash-count output space overflowed repeatedly");
 }
 
+// Hash keys, k <= 32, binned path (s2_bin.cu): pass A hashes every k-mer once and appends its 16-bit in-bin offset to the
+// region of its (window, bin); pass B counts each bin in shared memory and emits the survivors in order.  Window v is
+// partition v of `sample`, or (win_sample[v], win_part[v]) in the multi-GPU single pass.  Returns KMX_BIN_FALLBACK when
+// the data defeats the uniform bin regions (one slot holding a large share of a window): the caller takes the L2 path.
+static const int KMX_BIN_FALLBACK = -1002;
+static bool hash_binned_usable(const kmx_ctx* ctx)
+{
+  if (ctx->prm.key_kind != KMX_KEY_HASH || ctx->W != 1) return false;
+  if (kmx_env_flag("KMX_HASH_NOBIN") || kmx_env_flag("KMX_HIST_NOROLL") || kmx_env_flag("KMX_HIST_FUSE")) return false;   // A/B: L2-histogram kernels
+  const u64 Wb = ctx->prm.window_bits;
+  if (Wb >= (1ULL << 30)) return false;                    // hb_hash_mod: r < 3 d must fit 32 bits
+  const u64 NB = (Wb + (1ULL << 14) - 1) >> 14;            // bins per window with 32-bit counters (the finer split)
+  return NB <= hash_bin_max_bins() && (u64)ctx->prm.nb_partitions * NB <= (1ULL << 22);
+}
+
+static int count_hash_binned(Lane* ln, uint32_t sample, uint32_t hard_min, const u32* win_sample = nullptr, const u32* win_part = nullptr)
+{
+  kmx_ctx* ctx = ln->ctx;
+  const u32 P = ctx->prm.nb_partitions;
+  const u64 Wb = ctx->prm.window_bits;
+  const u32 TR = hash_bin_tile_records();
+  bool h16; double slack;
+  { std::lock_guard<std::mutex> g(ctx->mu); h16 = ctx->hist16 && !kmx_env_flag("KMX_HIST32"); slack = ctx->bin_slack; }
+  CK(ensure_pin(ln, (size_t)P * 32 + 512));
+  char* hp = ln->h_pin;
+  u64* r_loff = (u64*)hp;                                   // read-back: list_off[P] | meta[4] | flags[4]
+  u64* u_meta = (u64*)(hp + (size_t)P * 8 + 64);            // upload: meta[4] | flags[4]
+  u64* u_base = (u64*)(hp + (size_t)P * 8 + 128);           // upload: win_base[P] | tile_pref[P+1] | win_cap[P] | win_part[P]
+  u32* u_tpref = (u32*)(u_base + P); u32* u_cap = u_tpref + (P + 1); u32* u_wpart = u_cap + P;
+  const size_t up_bytes = (((size_t)P * 8 + ((size_t)3 * P + 1) * 4) + 7) & ~(size_t)7;
+  u64 cap = std::max<u64>(4096, ln->d_est);
+  for (int attempt = 0; attempt < 8; attempt++) {
+    const u32 bs_log = h16 ? 15u : 14u;
+    const u32 NB = (u32)((Wb + (1ULL << bs_log) - 1) >> bs_log);
+    const size_t items = (size_t)P * NB;
+    u64 ent = 0, tiles = 0;
+    for (u32 v = 0; v < P; v++) {
+      const u64 kc = ln->h_kcnt[v];
+      u64 c = kc ? (u64)((double)kc / NB * slack) + 512 : 0;
+      c = (c + 7) & ~(u64)7;
+      if (c * NB > 0xFFFFFFF0ULL) return KMX_BIN_FALLBACK;    // in-window entry offsets are 32-bit
+      u_base[v] = ent; u_cap[v] = (u32)c; ent += c * NB;
+      u_tpref[v] = (u32)tiles; tiles += ((u64)ln->h_cursor[v] + TR - 1) / TR;
+    }
+    if (tiles >= 0x7FFFFFF0ULL) return KMX_BIN_FALLBACK;
+    u_tpref[P] = (u32)tiles;
+    if (win_part) memcpy(u_wpart, win_part, (size_t)P * 4);
+    CK(ensure(ln, ln->binbuf, ent * 2 + 256));
+    // device meta: [status u64[items] | bin_cursor u32[items] | tickets u32[2]] zeroed per sample; layout upload; results
+    const size_t zbytes = (items * 12 + 8 + 15) & ~(size_t)15;
+    CK(ensure(ln, ln->binmeta, zbytes + up_bytes + (size_t)P * 8 + 64));
+    char* dm = (char*)ln->binmeta.p;
+    void* kp = nullptr; void* cp = nullptr;
+    CK(arena_alloc(ctx, cap * 8, &kp));
+    CK(arena_alloc(ctx, cap * 4, &cp));
+    HashBinArgs a;
+    a.records = ln->records.p; a.boff = ln->d_boff; a.bcnt = ln->d_cursor;
+    a.k = (int)ctx->prm.kmer_size; a.nwin = P; a.Wbits = Wb; a.NB = NB; a.bs_log = bs_log;
+    a.status = (u64*)dm; a.bin_cursor = (u32*)(dm + items * 8); a.tickets = a.bin_cursor + items;
+    a.win_base = (const u64*)(dm + zbytes); a.tile_pref = (const u32*)(a.win_base + P); a.win_cap = a.tile_pref + (P + 1);
+    a.win_part = win_part ? a.win_cap + P : nullptr;
+    a.list_off = (u64*)(dm + zbytes + up_bytes); a.meta = a.list_off + P; a.flags = (u32*)(a.meta + 4);
+    a.binbuf = (uint16_t*)ln->binbuf.p; a.out_keys = (u64*)kp; a.out_counts = (u32*)cp; a.hard_min = hard_min ? hard_min : 1;
+    u_meta[0] = 0; u_meta[1] = 0; u_meta[2] = cap; u_meta[3] = 0; u_meta[4] = 0; u_meta[5] = 0;
+    { PROF(KMX_PROF_HASH_HIST);
+      CK(cudaMemsetAsync(dm, 0, zbytes, ln->st));
+      CK(cudaMemcpyAsync(dm + zbytes, u_base, up_bytes, cudaMemcpyHostToDevice, ln->st));
+      CK(cudaMemcpyAsync(a.meta, u_meta, 48, cudaMemcpyHostToDevice, ln->st));
+      CK(launch_hash_binned(a, (u32)tiles, 0, h16, ln->st, &ln->launches)); }
+    { PROF(KMX_PROF_HASH_EMIT);
+      CK(launch_hash_binned(a, (u32)tiles, 1, h16, ln->st, &ln->launches)); }
+    CK(cudaMemcpyAsync(r_loff, a.list_off, (size_t)P * 8 + 48, cudaMemcpyDeviceToHost, ln->st));
+    CK(cudaStreamSynchronize(ln->st));
+    const u64 D = r_loff[P];
+    const u32* fl = (const u32*)(r_loff + P + 4);
+    if (fl[2]) {                                            // a bin region overflowed: more room, then the L2-histogram path
+      slack *= 2;
+      if (slack > 8.0) return KMX_BIN_FALLBACK;
+      { std::lock_guard<std::mutex> g(ctx->mu); ctx->bin_slack = std::max(ctx->bin_slack, slack); }
+      continue;
+    }
+    if (h16 && fl[1]) {                                     // a 16-bit counter wrapped: 32-bit counters from now on
+      { std::lock_guard<std::mutex> g(ctx->mu); ctx->hist16 = false; }
+      h16 = false;
+      continue;
+    }
+    ln->d_est = std::max<u64>(ln->d_est, D + D / 4 + 1024);
+    if (fl[0]) { cap = D + 1024; continue; }                // exact size now known
+    for (u32 v = 0; v < P; v++) {
+      if (win_part && ln->h_cursor[v] == 0) continue;       // unused window
+      const u32 smp = win_sample ? win_sample[v] : sample, prt = win_part ? win_part[v] : v;
+      ListRef& L = ctx->lists[(size_t)smp * P + prt];
+      const u64 end = v + 1 < P ? r_loff[v + 1] : D;
+      L.lo = (u64*)kp + r_loff[v]; L.hi = nullptr; L.cnt = (u32*)cp + r_loff[v]; L.n = end - r_loff[v];
+    }
+    ctx->stat[KMX_STAT_HASH_BINNED]++;
+    return KMX_OK;
+  }
+  return fail(ln, KMX_ERR_CUDA, "binned hash-count did not converge");
+}
+
 static int count_sample(Lane* ln, uint32_t sample, uint32_t hard_min)
 {
   kmx_ctx* ctx = ln->ctx;
   if (sample >= ctx->prm.nb_samples) return fail(ln, KMX_ERR_ARG, "sample %u >= nb_samples", sample);
   if (!ln->sample_ready) return fail(ln, KMX_ERR_STATE, "kmx_count_sample needs a sample finished by kmx_superk_end");
+  if (hash_binned_usable(ctx)) {
+    int rc = count_hash_binned(ln, sample, hard_min);
+    if (rc != KMX_BIN_FALLBACK) return rc;
+  }
   if (ctx->prm.key_kind == KMX_KEY_HASH) {
     size_t hist_bytes = (size_t)ctx->prm.nb_partitions * ctx->prm.window_bits * 4;
     int ok;

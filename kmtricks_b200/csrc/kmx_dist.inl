@@ -139,7 +139,8 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
   DBuf save_rec = ln->records;
   std::vector<u64> save_boff = ln->h_boff, save_kcnt = ln->h_kcnt; std::vector<u32> save_bcap = ln->h_bcap, save_cur = ln->h_cursor;
   const u32 Pown = myl - myf;
-  const bool hist_path = ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok == 1;
+  const bool binned = hash_binned_usable(ctx);
+  const bool hist_path = ctx->prm.key_kind == KMX_KEY_HASH && (ctx->hist_ok == 1 || binned);
   if (hist_path && (u64)G * Pown <= P && Pown > 0) {
     // ONE pass: histogram window v = g*Pown + (p - myf) holds partition p of rank g's sample; all
     // hard-mins of a batch are equal in practice, otherwise fall through to the per-source passes
@@ -162,9 +163,15 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
       rc = upload_bucket_meta(ln);
       ln->sample_ready = true;
       for (int g = 0; g < G; g++) for (u32 p = 0; p < P; p++) ctx->lists[((size_t)g * n_local + i_local) * P + p] = ListRef();
-      if (!rc) rc = count_hash_hist(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data());
-      ln->records = save_rec; ln->h_boff = save_boff; ln->h_kcnt = save_kcnt; ln->h_bcap = save_bcap; ln->h_cursor = save_cur;
-      return rc;
+      if (!rc) {
+        rc = binned ? count_hash_binned(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data()) : KMX_BIN_FALLBACK;
+        if (rc == KMX_BIN_FALLBACK && ctx->hist_ok == 1) rc = count_hash_hist(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data());
+      }
+      if (rc != KMX_BIN_FALLBACK) {
+        ln->records = save_rec; ln->h_boff = save_boff; ln->h_kcnt = save_kcnt; ln->h_bcap = save_bcap; ln->h_cursor = save_cur;
+        return rc;
+      }
+      rc = KMX_OK;                                       // neither single-pass path took it: per-source passes below
     }
   }
   for (int g = 0; g < G && !rc; g++) {

@@ -79,6 +79,29 @@ cudaError_t launch_hash_group(const S2Common& c, u64 Wbits, u64 mod_d, u64 mod_m
                               u64* out_keys, u32* out_counts, const u32* win_part, cudaStream_t st, u64* launches, int phase, bool h16);
 cudaError_t launch_scan_u32(const u32* in, u64* out, u64 n, u64* total, cudaStream_t st, u64* launches);
 
+// hash keys, k <= 32: binned shared-memory counting (s2_bin.cu).  "Window" v = one (sample, partition) bucket region.
+struct HashBinArgs {
+  const void* records; const u64* boff; const u32* bcnt;   // [nwin] device: bucket region of every window
+  int k; u32 nwin;
+  u64 Wbits; u32 NB, bs_log;      // slots per window, bins per window, log2(slots per bin)
+  const u32* tile_pref;           // [nwin+1] device: tiles of hash_bin_tile_records() records before window v
+  const u64* win_base;            // [nwin] device: first bin-buffer entry of window v (multiple of 8)
+  const u32* win_cap;             // [nwin] device: entries per bin of window v (multiple of 8)
+  u32* bin_cursor;                // [nwin*NB] zeroed: entries appended per bin (keeps counting past win_cap)
+  uint16_t* binbuf;               // 16-bit slot offsets, grouped by (window, bin)
+  u64* status;                    // [nwin*NB] zeroed: look-back words of pass B
+  u32* tickets;                   // [2] zeroed
+  u32* flags;                     // [0] output space ran out [1] a 16-bit counter wrapped [2] a bin region overflowed
+  u64* list_off;                  // [nwin] out: first output entry of window v
+  u64* meta;                      // [0] out: total entries, [2] in: output capacity
+  u64* out_keys; u32* out_counts;
+  const u32* win_part;            // NULL: window v holds partition v
+  u32 hard_min;
+};
+u32 hash_bin_max_bins();
+u32 hash_bin_tile_records();
+cudaError_t launch_hash_binned(const HashBinArgs& a, u32 total_tiles, int phase, bool h16, cudaStream_t st, u64* launches);
+
 // generic path: expand -> keys, segmented radix sort, run-length
 cudaError_t launch_expand_keys(const S2Common& c, int key_kind, u64 Wbits, u64 mod_d, u64 mod_mlo, u64 mod_mhi,
                                const u64* koff /* [P] device: key offset of partition */,

@@ -240,6 +240,7 @@ def run_pipeline(samples: list[list[bytes]], cfg: Config, sample_hard_min: dict 
             out["merge_info"][p] = formats.merge_info(m["stats"])
         out["launches"] = eng.launches()
         out["s1_self_indexed"] = int(eng.lib.kmx_stat(eng.h, 0)); out["s1_indexed"] = int(eng.lib.kmx_stat(eng.h, 1))
+        out["hash_binned"] = int(eng.lib.kmx_stat(eng.h, 2))
     finally:
         eng.close()
     return out
@@ -269,6 +270,7 @@ def run_pipeline_lanes(texts: list[bytes], cfg: Config, lanes: int = 4, device: 
             out["matrices"][p] = eng.matrix_file(p, m)
             out["merge_info"][p] = formats.merge_info(m["stats"])
         out["launches"] = eng.launches()
+        out["hash_binned"] = int(eng.lib.kmx_stat(eng.h, 2))
     finally:
         eng.close()
     return out

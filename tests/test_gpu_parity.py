@@ -84,7 +84,20 @@ def test_many_samples_many_partitions(name, case, N):
     _compare(got, want, case["P"], N)
 
 
+def test_hash_keys_take_the_binned_path(synth_samples):
+    """Hash keys with k <= 32 are counted by the binned shared-memory kernels (s2_bin.cu), one pass per sample; k > 32 keeps
+    the L2-histogram path."""
+    got, want = _run_both(synth_samples, CASES["hash_count"])
+    _compare(got, want, CASES["hash_count"]["P"], len(synth_samples))
+    assert got["hash_binned"] == len(synth_samples)
+    got, _ = _run_both(synth_samples, CASES["k63_hash_bf"])
+    assert got["hash_binned"] == 0
+
+
 @pytest.mark.parametrize("flag,name", [
+    ("KMX_HASH_NOBIN", "hash_bf"),         # L2-histogram path (fallback of the binned counting; what k > 32 uses)
+    ("KMX_HASH_NOBIN", "hash_count"),
+    ("KMX_HIST32", "hash_bf"),             # 32-bit counters from the start (binned: 16 K-slot bins)
     ("KMX_HIST_NOROLL", "hash_bf"),        # k <= 32 histogram fill by the search-and-extract kernel (the k > 32 / fallback kernel)
     ("KMX_HIST_FUSE", "hash_bf"),          # opt-in fused fill + compact persistent kernel (done counters, fences)
     ("KMX_HIST_FUSE", "hash_count"),
@@ -218,6 +231,11 @@ def test_hash_mode_larger_sample_all_paths(monkeypatch):
     case = dict(k=31, P=6, mode="hash:bf:bin", hard_min=2, bloom_size=3_000_000)
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], len(samples))
+    assert got["hash_binned"] == len(samples)
+    monkeypatch.setenv("KMX_HASH_NOBIN", "1")
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    assert got["hash_binned"] == 0
     monkeypatch.setenv("KMX_HIST_FUSE", "1")
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], len(samples))

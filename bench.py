@@ -51,8 +51,12 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4, help="samples in flight (kmx_run_samples lanes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-samples", type=int, default=8, help="samples in the bounded CPU-reference run")
-    ap.add_argument("--ref-reads", type=int, default=250_000)
+    ap.add_argument("--ref-samples", type=int, default=0, help="samples in the bounded CPU-reference run (0 = one per host thread, at most 16: "
+                                                               "the reference parses a sample on ONE thread, fewer samples leave cores idle)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="reads per sample of the CPU-reference run (0 = the workload's own, scaled down only "
+                                                             "when steps+warmup would push the run past --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle-checked pass after timing")
     return ap.parse_args()
 
 
@@ -150,6 +154,19 @@ def n_kmers(args):
 
 
 # --------------------------------------------------------------------------- reference arm
+def size_reference_run(args, nruns):
+    """Fills args.ref_samples / args.ref_reads: the workload's own per-sample shape when the whole run (nruns pipeline runs)
+    fits --ref-budget-s at ~8e7 k-mers/s, else fewer reads per sample (stated in the line)."""
+    threads = os.cpu_count() or 1
+    if args.ref_samples <= 0:
+        args.ref_samples = max(2, min(16, threads, args.samples))
+    if args.ref_reads <= 0:
+        per_read = args.read_len - args.kmer_size + 1
+        fit = args.ref_budget_s / max(nruns, 1) * 8.0e7 / (per_read * args.ref_samples)
+        args.ref_reads = int(max(100_000, min(args.reads, fit // 50_000 * 50_000)))
+    return args.ref_samples * args.ref_reads == args.samples * args.reads
+
+
 def run_reference_once(args, workdir, threads):
     """One bounded run of the unmodified reference pipeline; returns (seconds, kmers)."""
     from oracle import oracle as O
@@ -158,7 +175,7 @@ def run_reference_once(args, workdir, threads):
     shutil.rmtree(rd, ignore_errors=True)
     kind, what = args.mode.split(":")[:2]
     # same per-partition window as the full workload: bloom scaled to keep W
-    cmd = [O.REF_BIN, "pipeline", "--file", fof, "--run-dir", rd, "--kmer-size", str(args.kmer_size),
+    cmd = [O.timed_ref_bin()[0], "pipeline", "--file", fof, "--run-dir", rd, "--kmer-size", str(args.kmer_size),
            "--mode", f"{kind}:{what}:bin", "--hard-min", str(args.hard_min), "--nb-partitions", str(args.partitions),
            "--minimizer-size", "10", "--static-repart", "--bloom-size", str(args.bloom_size), "-t", str(threads)]
     t0 = time.perf_counter()
@@ -200,12 +217,14 @@ def cpu_baseline(args):
         return {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/bin/kmtricks missing"}
     wd = ref_workdir()
     try:
+        size_reference_run(args, 2)
         make_ref_inputs(args, wd)
         threads = os.cpu_count() or 1
         dt, km = run_reference_once(args, wd, threads)
         return {"value": km / dt, "unit": "k-mers/s", "cores": threads, "kind": "reference",
                 "sample": f"{args.ref_samples} samples x {args.ref_reads} reads x {args.read_len} nt of the same generator, "
-                          f"kmtricks pipeline --mode {args.mode} -t {threads} on {wd.split('/')[1]}, {dt:.2f} s wall incl. file I/O"}
+                          f"kmtricks pipeline --mode {args.mode} -t {threads} on {wd.split('/')[1]}, {dt:.2f} s wall incl. file I/O; "
+                          f"binary built {O.timed_ref_bin()[1]}"}
     finally:
         shutil.rmtree(wd, ignore_errors=True)
 
@@ -215,8 +234,13 @@ def main_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
+    same = size_reference_run(args, args.steps + args.warmup)
     cfg = {"workload": workload_name(args, int(os.environ.get("WORLD_SIZE", "1"))),
-           "sample": f"each step = {args.ref_samples} samples x {args.ref_reads} reads of that workload's generator (bounded so the run ends in minutes)",
+           "sample": f"each step = {args.ref_samples} samples x {args.ref_reads} reads x {args.read_len} nt of that workload's generator "
+                     f"(same k / P / bloom / hard-min / mode; one sample per host thread keeps every core busy; bounded so that "
+                     f"{args.steps}+{args.warmup} runs end within ~{int(args.ref_budget_s)} s)",
+           "same_config": bool(same), "same_per_sample_shape": args.ref_reads == args.reads,
+           "reference_build": O.timed_ref_bin()[1], "host_threads": os.cpu_count() or 1,
            "l2": "inputs larger than L2"}
     if not O.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/kmtricks not built (run oracle/build_ref.sh where /root/reference exists)"}))
@@ -237,7 +261,7 @@ def main_reference(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                                 "sample": f"{args.ref_samples} x {args.ref_reads} reads per step, files on {wd.split('/')[1]}"},
+                                 "sample": f"{args.ref_samples} x {args.ref_reads} reads per step, files on {wd.split('/')[1]}, binary built {O.timed_ref_bin()[1]}"},
                 "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -377,11 +401,15 @@ def main_kmx(args):
 
     # per-kernel device time: same step, ONE lane (kernels back to back on one stream, so the
     # CUDA-event spans around each launch are exclusive), events recorded inside the library
+    if world > 1:
+        ck(L.kmx_dist_set_lanes(h, 1), "dist_set_lanes")      # one lane: samples back to back on one stream, exclusive spans
     step_device_1lane()
     ck(L.kmx_profile_enable(h, 1), "prof")
     ck(L.kmx_profile_reset(h), "prof")
     psteps = max(1, min(args.steps, 2))
+    exch0 = int(L.kmx_stat(h, 4))
     ms_1lane = timed(step_device_1lane, psteps) / psteps
+    exch_bytes_step = (int(L.kmx_stat(h, 4)) - exch0) // psteps
     prof = {}
     for i, name in enumerate(_lib.PROF_KINDS):
         tms = C.c_double(); cnt = C.c_uint64()
@@ -389,6 +417,16 @@ def main_kmx(args):
         if cnt.value:
             prof[name] = {"ms_per_step": tms.value / psteps, "launches_per_step": cnt.value // psteps}
     ck(L.kmx_profile_enable(h, 0), "prof")
+    if world > 1:
+        ck(L.kmx_dist_set_lanes(h, args.lanes), "dist_set_lanes")
+    exchange = None
+    if world > 1 and "exchange" in prof:
+        # bytes this rank put on NVLink per step (its buckets for the other ranks' partitions) over the CUDA-event time of the
+        # grouped send/recv; 770 GB/s per direction is the measured peer-copy figure of B200_PROFILING.md (900 nominal)
+        ems = prof["exchange"]["ms_per_step"]
+        exchange = {"sent_bytes_per_step_rank0": exch_bytes_step, "ms_per_step": round(ems, 3), "GBps_per_direction": exch_bytes_step / (ems * 1e-3) / 1e9 if ems > 0 else None,
+                    "nvlink_peer_copy_GBps_measured": 770.0, "frac_of_nvlink": exch_bytes_step / (ems * 1e-3) / 1e9 / 770.0 if ems > 0 else None,
+                    "bytes_per_kmer": exch_bytes_step / kmers_step}
 
     # ---- roofline of the dominant kernel (device time share from the event spans)
     peaks = {}
@@ -398,7 +436,7 @@ def main_kmx(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kern_time = {k: v["ms_per_step"] for k, v in prof.items() if k not in ("fill",)}
+    kern_time = {k: v["ms_per_step"] for k, v in prof.items() if k not in ("fill", "exchange")}
     top = max(kern_time, key=kern_time.get) if kern_time else None
     roof = None
     if top:
@@ -491,6 +529,15 @@ def main_kmx(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
 
+    # ---- N > 1: the path just timed, on small seeded samples, against the CPU oracle (the checker; tests/dist_check.py)
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        try:
+            from tests import dist_check
+            parity = "ok" if dist_check.check(rank, world, local, quiet=True) else "FAIL"
+        except Exception as e:      # the check must not take the measurement down with it
+            parity = f"error: {e}"
+
     if rank == 0:
         line = {"metric": "k-mers/s end-to-end (repart->merge)", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -499,6 +546,7 @@ def main_kmx(args):
                            "kmers_per_step": kmers_step, "l2": "inputs larger than L2 (315 MB text per launch)",
                            "value_clock": "FASTQ resident in HBM -> all .cmbf bodies in HBM", "lanes": args.lanes},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "parity_check": parity, "exchange": exchange,
                 "kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in prof.items()}, "ms_per_step_1lane": ms_1lane,
                 "host_wall_ms_per_step": host_wall, "device_bytes": int(L.kmx_device_bytes(h))}
         print(json.dumps(line))

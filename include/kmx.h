@@ -151,6 +151,9 @@ int kmx_dist_init(kmx_ctx* ctx, int rank, int world, uint32_t nlanes, const uint
 int kmx_dist_owner(const kmx_ctx* ctx, uint32_t partition, int world);
 int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* const* texts, const size_t* nbytes, int on_device,
                          const uint32_t* hard_min, uint64_t* kmers_per_partition);
+/* how many of the communicators' lanes kmx_dist_run_samples uses (1..nlanes of kmx_dist_init; every rank the same
+ * value).  1 = samples strictly one after the other on one stream: the per-kernel profile spans are then exclusive.     */
+int kmx_dist_set_lanes(kmx_ctx* ctx, uint32_t nlanes);
 
 /* ---- utilities (benchmark / tests) ------------------------------------------------------ */
 /* device twin of kmtricks_b200/synth.py: writes R records of 2L+15 bytes to dev_out        */
@@ -181,7 +184,9 @@ uint64_t kmx_device_bytes(const kmx_ctx* ctx);
  * (no line-index pass) / blocks that went through the line index / hash-count passes on the binned path */
 enum { KMX_STAT_S1_SELF_INDEXED = 0, KMX_STAT_S1_INDEXED = 1,
        KMX_STAT_HASH_BINNED = 2,   /* samples counted by the binned shared-memory path (hash keys, k <= 32) */
-       KMX_STAT_KINDS = 3 };
+       KMX_STAT_S1_RETRY = 3,      /* stage-1 launches redone because a bucket region was too small */
+       KMX_STAT_EXCH_BYTES = 4,    /* bytes this rank sent through the bucket exchange (kmx_dist_run_samples) */
+       KMX_STAT_KINDS = 5 };
 uint64_t kmx_stat(const kmx_ctx* ctx, int which);
 
 #ifdef __cplusplus

@@ -47,6 +47,7 @@ SYMBOLS = {
     "kmx_dist_unique_id": (_i, [_vp]),
     "kmx_dist_init": (_i, [_vp, _i, _i, _u32, _vp]),
     "kmx_dist_owner": (_i, [_vp, _u32, _i]),
+    "kmx_dist_set_lanes": (_i, [_vp, _u32]),
     "kmx_dist_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u64)]),
     "kmx_counts_size": (_i, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "kmx_counts_get": (_i, [_vp, _u32, _u32, _vp, _vp]),

@@ -111,6 +111,7 @@ struct kmx_ctx {
   double bin_slack = 1.25;         // bin-region capacity over the mean bin load (doubles when a bin overflowed; > 8: L2-histogram path)
   int active_lanes = 1;            // lanes running concurrently (sizes the L2-resident histogram groups)
   std::atomic<u64> stat[KMX_STAT_KINDS];
+  std::vector<double> rec_rate;    // [P] bucket records per input byte, the most seen so far: sizes the bucket regions of the next sample
   u32 s1_len_hint = 0;             // longest FASTQ read seen so far: geometry of the self-indexing stage-1 launch (0 = none yet)
   double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
   bool ht_union_ok = true;
@@ -173,7 +174,36 @@ static void prof_collect(kmx_ctx* c)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ln, e_ == cudaErrorMemoryAllocation ? KMX_ERR_NOMEM : KMX_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// Small host<->device transfers by a KERNEL that reads / writes the lane's pinned scratch directly (cudaMallocHost memory
+// is device-accessible under unified addressing).  A cudaMemcpyAsync of a few hundred bytes queues on the copy engine
+// behind the 315 MB FASTQ copies of the other lanes and stalls its own lane for milliseconds; a kernel does not.
+struct SmallCopy { void* dst[4]; const void* src[4]; u32 n[4]; };
+__global__ void __launch_bounds__(256) kmx_small_copy_kernel(SmallCopy c)
+{
+  for (int s = 0; s < 4; s++) {
+    const u32 n = c.n[s];
+    if (!n) continue;
+    char* d = (char*)c.dst[s]; const char* a = (const char*)c.src[s];
+    if ((((uintptr_t)d | (uintptr_t)a | n) & 7u) == 0) { for (u32 i = threadIdx.x; i < n / 8; i += 256) ((u64*)d)[i] = ((const volatile u64*)a)[i]; }
+    else for (u32 i = threadIdx.x; i < n; i += 256) d[i] = ((const volatile char*)a)[i];
+  }
+}
+struct SmallCopyBatch {
+  Lane* ln; SmallCopy c; int k = 0;
+  explicit SmallCopyBatch(Lane* l) : ln(l) { memset(&c, 0, sizeof c); }
+  void add(void* dst, const void* src, size_t n) { c.dst[k] = dst; c.src[k] = src; c.n[k] = (u32)n; k++; }
+  cudaError_t go();
+};
+
 static void add_bytes(kmx_ctx* ctx, long long d) { std::lock_guard<std::mutex> g(ctx->mu); ctx->dev_bytes = (u64)((long long)ctx->dev_bytes + d); }
+
+cudaError_t SmallCopyBatch::go()
+{
+  if (!k) return cudaSuccess;
+  kmx_small_copy_kernel<<<1, 256, 0, ln->st>>>(c);
+  ln->launches += 1; k = 0; memset(&c, 0, sizeof c);
+  return cudaGetLastError();
+}
 
 static cudaError_t ensure(Lane* ln, DBuf& b, size_t bytes)
 {
@@ -293,6 +323,7 @@ extern "C" int kmx_create(int device, const kmx_params* prm, kmx_ctx** out)
   CK(cudaMemcpy(ctx->d_repart, prm->repart_table, tn * 2, cudaMemcpyHostToDevice));
   ctx->prm.repart_table = nullptr;
   ctx->lists.assign((size_t)prm->nb_samples * prm->nb_partitions, ListRef());
+  ctx->rec_rate.assign(prm->nb_partitions, 0.0);
   int rc = lane_create(ctx, 0);
   if (rc) return rc;
   return KMX_OK;
@@ -356,10 +387,10 @@ static int upload_bucket_meta(Lane* ln)
   char* hp = ln->h_pin;
   memcpy(hp, ln->h_boff.data(), P * 8); memcpy(hp + P * 8, ln->h_kcnt.data(), P * 8);
   memcpy(hp + P * 16, ln->h_bcap.data(), P * 4); memcpy(hp + P * 20, ln->h_cursor.data(), P * 4);
-  CK(cudaMemcpyAsync(ln->d_boff, hp, P * 8, cudaMemcpyHostToDevice, ln->st));
-  CK(cudaMemcpyAsync(ln->d_kcnt, hp + P * 8, P * 8, cudaMemcpyHostToDevice, ln->st));
-  CK(cudaMemcpyAsync(ln->d_bcap, hp + P * 16, P * 4, cudaMemcpyHostToDevice, ln->st));
-  CK(cudaMemcpyAsync(ln->d_cursor, hp + P * 20, P * 4, cudaMemcpyHostToDevice, ln->st));
+  SmallCopyBatch b(ln);
+  b.add(ln->d_boff, hp, P * 8); b.add(ln->d_kcnt, hp + P * 8, P * 8);
+  b.add(ln->d_bcap, hp + P * 16, P * 4); b.add(ln->d_cursor, hp + P * 20, P * 4);
+  CK(b.go());
   CK(cudaStreamSynchronize(ln->st));             // the scratch is reused right away
   return KMX_OK;
 }
@@ -396,6 +427,28 @@ static int grow_buckets(Lane* ln, const std::vector<u64>& need)
   return KMX_OK;
 }
 
+// a sample's first push: lay the regions out afresh, need[p] records each (nothing to keep), reusing the slab when it is big enough
+static int layout_buckets(Lane* ln, const std::vector<u64>& need)
+{
+  kmx_ctx* ctx = ln->ctx;
+  const u32 P = ctx->prm.nb_partitions;
+  const size_t rec = ctx->W == 1 ? 16 : 32;
+  u64 tot = 0;
+  for (u32 p = 0; p < P; p++) {
+    const u64 c = (need[p] + 63) & ~(u64)63;
+    if (c > 0xFFFFFFF0ULL) return fail(ln, KMX_ERR_NOMEM, "partition %u needs %llu records (> 2^32)", p, (unsigned long long)c);
+    ln->h_boff[p] = tot; ln->h_bcap[p] = (u32)c; tot += c;
+  }
+  if (tot * rec + 256 > ln->records.cap) {
+    if (ln->records.p) { CK(cudaStreamSynchronize(ln->st)); release(ctx, ln->records); }
+    const size_t cap = (size_t)((double)(tot * rec) * 1.1) + 256;
+    cudaError_t e = cudaMalloc(&ln->records.p, cap);
+    if (e != cudaSuccess) { ln->records.p = nullptr; return fail(ln, KMX_ERR_NOMEM, "bucket slab of %zu bytes: %s", cap, cudaGetErrorString(e)); }
+    ln->records.cap = cap; add_bytes(ctx, (long long)cap);
+  }
+  return KMX_OK;
+}
+
 static int superk_begin(Lane* ln)
 {
   std::fill(ln->h_cursor.begin(), ln->h_cursor.end(), 0u);
@@ -415,11 +468,22 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
   if (max_len > 2048) return fail(ln, KMX_ERR_FORMAT, "sequence of %u bases: stage 1 takes segments of <= 2048 bases (kmx_superk_push_reads splits long sequences)", max_len);
   kmx_ctx* ctx = ln->ctx;
   const u32 P = ctx->prm.nb_partitions;
-  // optimistic capacity: ~1 record per 8 k-mers, 30% head-room for partition imbalance
+  // Region capacities.  From the densest sample seen so far (records per input byte and partition, +15 %): the regions are
+  // then barely larger than what is written, which is also what the multi-GPU exchange ships.  Before any sample was seen:
+  // ~1 record per 8 k-mers, 30 % head-room for partition imbalance.  Too small -> the cursors keep counting, one retry.
   std::vector<u64> need(P);
-  for (u32 p = 0; p < P; p++) need[p] = (u64)ln->h_cursor[p] + (u64)((double)est_kmers / 8.0 / P * 1.3) + 1024;
+  bool fresh = true;
+  for (u32 p = 0; p < P; p++) if (ln->h_cursor[p]) fresh = false;
+  const std::vector<u32> cur0 = ln->h_cursor;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (u32 p = 0; p < P; p++) {
+      const double r = kmx_env_flag("KMX_S1_LOOSE") ? 0.0 : ctx->rec_rate[p];
+      need[p] = (u64)ln->h_cursor[p] + (r > 0 ? (u64)(r * (double)text_bytes * 1.15) + 512 : (u64)((double)est_kmers / 8.0 / P * 1.3) + 1024);
+    }
+  }
   for (int attempt = 0; attempt < 3; attempt++) {
-    int rc = grow_buckets(ln, need);
+    int rc = fresh ? layout_buckets(ln, need) : grow_buckets(ln, need);
     if (rc) return rc;
     rc = upload_bucket_meta(ln);
     if (rc) return rc;
@@ -440,14 +504,22 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
       } else if (s1_v5_usable(max_len, a.k, a.m, P, &geo, &smem5)) CK(launch_s1_v5(ctx->W, a, geo, smem5, nullptr, ln->st, &ln->launches));
       else CK(launch_s1(ctx->W, a, ln->st, &ln->launches)); }
     u64* kc = (u64*)ln->h_pin; u32* cur = (u32*)(ln->h_pin + P * 8); u32* ovf = (u32*)(ln->h_pin + P * 12);
-    CK(cudaMemcpyAsync(kc, ln->d_kcnt, P * 8, cudaMemcpyDeviceToHost, ln->st));
-    CK(cudaMemcpyAsync(cur, ln->d_cursor, P * 4, cudaMemcpyDeviceToHost, ln->st));
     u32* fl4 = (u32*)(ln->h_pin + P * 12 + 16);
-    CK(cudaMemcpyAsync(ovf, ln->d_flags + 2, 4, cudaMemcpyDeviceToHost, ln->st));
-    if (fi) CK(cudaMemcpyAsync(fl4, ln->d_flags, 16, cudaMemcpyDeviceToHost, ln->st));
+    { SmallCopyBatch b(ln);
+      b.add(kc, ln->d_kcnt, P * 8); b.add(cur, ln->d_cursor, P * 4); b.add(ovf, ln->d_flags + 2, 4);
+      if (fi) b.add(fl4, ln->d_flags, 16);
+      CK(b.go()); }
     CK(cudaStreamSynchronize(ln->st));
     if (fi && (fl4[0] || fl4[3])) return KMX_S1_FALLBACK;     // the device cursors are restored from the host snapshot by the next upload
-    if (!*ovf) { ln->h_cursor.assign(cur, cur + P); ln->h_kcnt.assign(kc, kc + P); return KMX_OK; }
+    if (!*ovf) {
+      ln->h_cursor.assign(cur, cur + P); ln->h_kcnt.assign(kc, kc + P);
+      if (text_bytes >= 4096) {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        for (u32 p = 0; p < P; p++) ctx->rec_rate[p] = std::max(ctx->rec_rate[p], (double)(cur[p] - cur0[p]) / (double)text_bytes);
+      }
+      return KMX_OK;
+    }
+    ctx->stat[KMX_STAT_S1_RETRY]++;
     // exact sizes are now known (the cursors kept counting); redo this push from the snapshot
     for (u32 p = 0; p < P; p++) need[p] = (u64)cur[p] + 64;
   }
@@ -472,8 +544,7 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   CK(ensure(ln, ln->nlmask, ntiles * 256 * 8));             // one bit per text byte, whole 16 KiB tiles
   { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, (u64*)ln->nlmask.p, ln->d_total, nullptr, nullptr, 0, nullptr, 0, ln->st, &ln->launches)); }
   u64* nl = (u64*)ln->h_pin; uint8_t* last = (uint8_t*)(ln->h_pin + 8);
-  CK(cudaMemcpyAsync(nl, ln->d_total, 8, cudaMemcpyDeviceToHost, ln->st));
-  CK(cudaMemcpyAsync(last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ln->st));
+  { SmallCopyBatch b(ln); b.add(nl, ln->d_total, 8); b.add(last, d_text + nbytes - 1, 1); CK(b.go()); }
   CK(cudaStreamSynchronize(ln->st));
   u64 nlines = *nl + (*last != '\n' ? 1 : 0);
   if (nlines % 4) return fail(ln, KMX_ERR_FORMAT, "FASTQ block has %llu lines (not a multiple of 4)", (unsigned long long)nlines);
@@ -501,7 +572,7 @@ static int superk_push_fastq(Lane* ln, const char* text, size_t nbytes, int on_d
   { PROF(KMX_PROF_INDEX); CK(launch_fq_index(d_text, nbytes, (u32*)ln->tile_counts.p, (u64*)ln->tile_prefix.p, (u64*)ln->nlmask.p, ln->d_total,
                      (u32*)ln->seq_start.p, (u32*)ln->seq_len.p, nrec, ln->d_flags, 1, ln->st, &ln->launches)); }
   u32* fl = (u32*)ln->h_pin;
-  CK(cudaMemcpyAsync(fl, ln->d_flags, 8, cudaMemcpyDeviceToHost, ln->st));
+  { SmallCopyBatch b(ln); b.add(fl, ln->d_flags, 8); CK(b.go()); }
   CK(cudaStreamSynchronize(ln->st));
   if (fl[0]) return fail(ln, KMX_ERR_FORMAT, "text is not strict 4-line FASTQ");
   const u32 block_max = fl[1];
@@ -628,7 +699,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
   if (win_part) {
     u32* hp = (u32*)(ln->h_pin + (size_t)P * 8 + 64);
     memcpy(hp, win_part, (size_t)P * 4);
-    CK(cudaMemcpyAsync(d_wpart, hp, (size_t)P * 4, cudaMemcpyHostToDevice, ln->st));
+    { SmallCopyBatch b(ln); b.add(d_wpart, hp, (size_t)P * 4); CK(b.go()); }
     dwp = d_wpart;
   }
   u64 cap = std::max<u64>(4096, ln->d_est);
@@ -638,7 +709,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
     CK(arena_alloc(ctx, cap * 4, &cp));
     u64* hm = (u64*)(ln->h_pin + (size_t)P * 8);             // staging for meta = {cursor, cursor', capacity, -} + flags
     hm[0] = 0; hm[1] = 0; hm[2] = cap; hm[3] = 0; hm[4] = 0;
-    CK(cudaMemcpyAsync(d_meta, hm, 40, cudaMemcpyHostToDevice, ln->st));    // meta[4] + flags[2]
+    { SmallCopyBatch b(ln); b.add(d_meta, hm, 40); CK(b.go()); }            // meta[4] + flags[2]
     u32 ngroups = 0;
     for (u32 p0 = 0; p0 < P; p0 += gp, ngroups++) {
       const u32 g = std::min(gp, P - p0);
@@ -650,7 +721,7 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
                              d_meta, d_flags, (u64*)kp, (u32*)cp, dwp, ln->st, &ln->launches, 1, h16)); }
     }
     u64* h_l = (u64*)ln->h_pin;                               // list_off[P] then meta[4], flags[2]
-    CK(cudaMemcpyAsync(h_l, d_loff, (size_t)P * 8 + 40, cudaMemcpyDeviceToHost, ln->st));
+    { SmallCopyBatch b(ln); b.add(h_l, d_loff, (size_t)P * 8 + 40); CK(b.go()); }
     CK(cudaStreamSynchronize(ln->st));
     const u64 D = h_l[P + (ngroups & 1u)];
     const u32 ovf = *(u32*)(h_l + P + 4), wrapped = *((u32*)(h_l + P + 4) + 1);
@@ -741,12 +812,11 @@ static int count_hash_binned(Lane* ln, uint32_t sample, uint32_t hard_min, const
     u_meta[0] = 0; u_meta[1] = 0; u_meta[2] = cap; u_meta[3] = 0; u_meta[4] = 0; u_meta[5] = 0;
     { PROF(KMX_PROF_HASH_HIST);
       CK(cudaMemsetAsync(dm, 0, zbytes, ln->st));
-      CK(cudaMemcpyAsync(dm + zbytes, u_base, up_bytes, cudaMemcpyHostToDevice, ln->st));
-      CK(cudaMemcpyAsync(a.meta, u_meta, 48, cudaMemcpyHostToDevice, ln->st));
+      { SmallCopyBatch b(ln); b.add(dm + zbytes, u_base, up_bytes); b.add(a.meta, u_meta, 48); CK(b.go()); }
       CK(launch_hash_binned(a, (u32)tiles, 0, h16, ln->st, &ln->launches)); }
     { PROF(KMX_PROF_HASH_EMIT);
       CK(launch_hash_binned(a, (u32)tiles, 1, h16, ln->st, &ln->launches)); }
-    CK(cudaMemcpyAsync(r_loff, a.list_off, (size_t)P * 8 + 48, cudaMemcpyDeviceToHost, ln->st));
+    { SmallCopyBatch b(ln); b.add(r_loff, a.list_off, (size_t)P * 8 + 48); CK(b.go()); }
     CK(cudaStreamSynchronize(ln->st));
     const u64 D = r_loff[P];
     const u32* fl = (const u32*)(r_loff + P + 4);
@@ -956,8 +1026,7 @@ extern "C" int kmx_merge_partition(kmx_ctx* ctx, uint32_t partition, const kmx_m
   CK(ensure(ln, ctx->d_lists, N * sizeof(MergeList)));
   CK(ensure(ln, ctx->d_soft, N * 4));
   CK(ensure(ln, ctx->stats, (size_t)6 * N * 8));
-  CK(cudaMemcpyAsync(ctx->d_lists.p, hl_pin, N * sizeof(MergeList), cudaMemcpyHostToDevice, ln->st));
-  CK(cudaMemcpyAsync(ctx->d_soft.p, soft_pin, N * 4, cudaMemcpyHostToDevice, ln->st));
+  { SmallCopyBatch b(ln); b.add(ctx->d_lists.p, hl_pin, N * sizeof(MergeList)); b.add(ctx->d_soft.p, soft_pin, N * 4); CK(b.go()); }
   CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)6 * N * 8, ln->st));
   ctx->last_emit_all = mp->emit_all;
   if (mp->format == KMX_FMT_COUNT || mp->format == KMX_FMT_PA) return merge_sparse(ln, partition, mp, res, hl, max_n, tot_n);

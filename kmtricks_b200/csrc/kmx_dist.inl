@@ -42,6 +42,7 @@ static const char* nccl_load()
 
 struct KmxDist {
   int rank = 0, world = 1;
+  u32 use_lanes = 0;                      // 0 = all
   std::vector<ncclComm_t> comms;          // one per lane
   std::vector<DBuf> recv, meta_dev;       // per lane
 };
@@ -80,6 +81,13 @@ extern "C" int kmx_dist_init(kmx_ctx* ctx, int rank, int world, uint32_t nlanes,
   return KMX_OK;
 }
 
+extern "C" int kmx_dist_set_lanes(kmx_ctx* ctx, uint32_t nlanes)
+{
+  if (!ctx || !ctx->dist || nlanes < 1 || nlanes > ctx->dist->comms.size()) return KMX_ERR_ARG;
+  ctx->dist->use_lanes = nlanes;
+  return KMX_OK;
+}
+
 extern "C" int kmx_dist_owner(const kmx_ctx* ctx, uint32_t partition, int world)
 {
   if (!ctx || world < 1 || partition >= ctx->prm.nb_partitions) return -1;
@@ -101,22 +109,28 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
   int rc = superk_begin(ln);
   if (!rc) rc = superk_push_fastq(ln, text, nbytes, on_device);
   if (!rc) rc = superk_end(ln, pinfo_out);
-  if (rc) return rc;
-  // ---- geometry all-gather: [boff[P+1] | cursor[P] | kcnt[P] | hard_min] as u64
-  const size_t ML = (size_t)3 * P + 2;
+  // a rank that failed still takes part in the geometry all-gather (with its status), so that all ranks stop together
+  // instead of the others waiting forever in the exchange
+  const int rc_local = rc;
+  // ---- geometry all-gather: [boff[P+1] | cursor[P] | kcnt[P] | hard_min | status] as u64
+  const size_t ML = (size_t)3 * P + 3;
   CK(ensure_pin(ln, (size_t)(G + 1) * ML * 8 + 256));
   CK(ensure(ln, d->meta_dev[lane_idx], (size_t)(G + 1) * ML * 8));
   u64* hm = (u64*)ln->h_pin;
   for (u32 p = 0; p < P; p++) { hm[p] = ln->h_boff[p]; hm[P + 1 + p] = ln->h_cursor[p]; hm[2 * P + 1 + p] = ln->h_kcnt[p]; }
   hm[P] = P ? ln->h_boff[P - 1] + ln->h_bcap[P - 1] : 0;
   hm[3 * P + 1] = hard_min;
+  hm[3 * P + 2] = (u64)(u32)rc_local;
+  if (rc_local) for (size_t i = 0; i < (size_t)3 * P + 1; i++) hm[i] = 0;
   u64* dm = (u64*)d->meta_dev[lane_idx].p;
-  CK(cudaMemcpyAsync(dm, hm, ML * 8, cudaMemcpyHostToDevice, ln->st));
+  { SmallCopyBatch b(ln); b.add(dm, hm, ML * 8); CK(b.go()); }
   NK(g_nccl.AllGather(dm, dm + ML, ML * 8, ncclUint8, comm, ln->st));
   u64* all = hm + ML;
-  CK(cudaMemcpyAsync(all, dm + ML, (size_t)G * ML * 8, cudaMemcpyDeviceToHost, ln->st));
+  { SmallCopyBatch b(ln); b.add(all, dm + ML, (size_t)G * ML * 8); CK(b.go()); }
   CK(cudaStreamSynchronize(ln->st));
   std::vector<u64> meta(all, all + (size_t)G * ML);      // the pinned scratch is reused below
+  if (rc_local) return rc_local;
+  for (int g = 0; g < G; g++) if (meta[(size_t)g * ML + 3 * P + 2]) return fail(ln, KMX_ERR_STATE, "rank %d failed in stage 1 of this batch (status %u)", g, (unsigned)meta[(size_t)g * ML + 3 * P + 2]);
   // ---- payload: my slab region of g's partitions -> g ; g's region of my partitions -> me
   const u32 myf = part_first(P, G, me), myl = part_first(P, G, me + 1);
   std::vector<u64> roff(G + 1, 0);
@@ -131,6 +145,7 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
       const u32 gf = part_first(P, G, g), gl = part_first(P, G, g + 1);
       const u64 sbytes = (mm[gl] - mm[gf]) * rec, rbytes = (roff[g + 1] - roff[g]) * rec;
       if (sbytes) NK(g_nccl.Send((const char*)ln->records.p + mm[gf] * rec, sbytes, ncclUint8, g, comm, ln->st));
+      if (g != me) ctx->stat[KMX_STAT_EXCH_BYTES] += sbytes;
       if (rbytes) NK(g_nccl.Recv(rbuf + roff[g] * rec, rbytes, ncclUint8, g, comm, ln->st));
     }
     NK(g_nccl.GroupEnd());
@@ -198,7 +213,7 @@ extern "C" int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* 
   if (!ctx || !ctx->dist || (n_local && (!texts || !nbytes || !hard_min))) return KMX_ERR_ARG;
   KmxDist* d = ctx->dist.get();
   const u32 P = ctx->prm.nb_partitions;
-  const u32 nlanes = (u32)d->comms.size();
+  const u32 nlanes = d->use_lanes ? std::min<u32>(d->use_lanes, (u32)d->comms.size()) : (u32)d->comms.size();
   {
     LANE0;
     if ((u64)d->world * n_local > ctx->prm.nb_samples) return fail(ln, KMX_ERR_ARG, "nb_samples %u < world %d x n_local %u", ctx->prm.nb_samples, d->world, n_local);

@@ -81,6 +81,7 @@ __device__ __forceinline__ u32 hb_saddr(const void* p) { return (u32)__cvta_gene
 __device__ __forceinline__ u32 hb_atoms_inc(u32 addr) { u32 r; asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(addr) : "memory"); return r; }
 __device__ __forceinline__ void hb_sts16(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ u32 hb_lds16(u32 addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ u32 hb_lds32(u32 addr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
 // NBMAX: capacity of the per-bin arrays (static shared memory).  FAST: 28 <= k <= 32 -- the bases after a record's first
 // k-mer fit one 64-bit word and the roll runs on 32-bit halves with the k-dependent shifts folded into constants.
@@ -105,6 +106,7 @@ hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
   const u32 khmask = (u32)(kmask >> 32);              // FAST: 2k > 32
   const u32 rs = (u32)(rcsh - 32) & 31u, rc2 = 2u << rs;
   const u32 a_bcnt = hb_opaque32(hb_saddr(s_bcnt)), a_stage = hb_opaque32(hb_saddr(s_stage));
+  const u32 a_gcnt = hb_opaque32(hb_saddr(s_gcnt)), a_gdst = hb_opaque32(hb_saddr(s_gdst));
   const u64 p4 = hb_opaque64(KMX_P4);
   const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(a.records);
   // persistent, in-order tickets over (window, tile) items numbered window-major (tile_pref = prefix of tiles per window)
@@ -253,8 +255,8 @@ hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
       __syncthreads();
       // ---- append every bin's run to its region (coalesced 2-byte runs)
       for (u32 b = w; b < NB; b += HB_WARPS) {
-        const u32 c = s_gcnt[b];
-        const u32 d = s_gdst[b];
+        const u32 c = hb_lds32(a_gcnt + b * 4u);
+        const u32 d = hb_lds32(a_gdst + b * 4u);
         const u32 sa = a_stage + b * C * 2u;
 #pragma unroll 1
         for (u32 j = lane; j < c; j += 32u) wp[d + j] = (uint16_t)hb_lds16(sa + j * 2u);
@@ -303,12 +305,11 @@ __global__ void __launch_bounds__(HC2_THREADS, 3)
 hash_bincount_kernel(HashBinArgs a)
 {
   extern __shared__ __align__(16) u32 s_h[];                    // [HC2_WORDS_P]
-  __shared__ u32 s_wtot[HC2_WARPS], s_wfs[HC2_WARPS], s_item;
+  __shared__ u32 s_wtot[HC2_WARPS], s_wfs[HC2_WARPS];
   __shared__ u64 s_excl;
   const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  if (tid == 0) s_item = atomicAdd(a.tickets + 1, 1u);           // in-order tickets: every predecessor of a running CTA is running or done
-  __syncthreads();
-  const u32 item = s_item;
+  // CTAs are dispatched in block-index order, so every predecessor a CTA looks back at is running or done
+  const u32 item = blockIdx.x;
   const u32 v = item / a.NB, b = item - v * a.NB;
   const u32 cap = __ldg(a.win_cap + v);
   const u32 n = min(a.bin_cursor[item], cap);

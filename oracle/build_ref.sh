@@ -8,15 +8,19 @@
 # values the reference's CMakeLists would have substituted (CMakeLists.txt:30-41,112;
 # thirdparty/gatb-core-stripped/CMakeLists.txt "configure_file" block).
 #
-# Usage: oracle/build_ref.sh [REF=/root/reference] [JOBS=nproc] [MARCH=]   (env vars)
+# Usage: oracle/build_ref.sh [REF=/root/reference] [JOBS=nproc] [MARCH=] [SUFFIX=]   (env vars)
+# SUFFIX=_v3 MARCH=-march=x86-64-v3 builds a second CLI binary bin/kmtricks_v3 (AVX2/BMI2/FMA code generation, what
+# the reference's -DNATIVE=ON gives on the bench hosts) for the timed CPU baseline; bench.py picks it when the host
+# CPU has those flags.  The default (portable) build is the parity oracle and also builds the harness and the plugins.
 set -euo pipefail
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 OUT=$HERE/_ref
 JOBS=${JOBS:-$(nproc)}
 MARCH=${MARCH:-}            # e.g. MARCH=-march=native for a timed baseline on the same box
+SUFFIX=${SUFFIX:-}
 [ -d "$REF/include/kmtricks" ] || { echo "reference not found at $REF" >&2; exit 3; }
-GEN=$OUT/gen; OBJ=$OUT/obj
+GEN=$OUT/gen; OBJ=$OUT/obj$SUFFIX
 mkdir -p "$GEN/include/kmtricks" "$GEN/include/gatb/system/api" "$GEN/src/gatb/template" "$GEN/kff" "$OBJ" "$OUT/bin"
 T=$REF/thirdparty; G=$T/gatb-core-stripped
 
@@ -135,8 +139,9 @@ export G GEN T INC CXXF MARCH REF
 xargs -a "$LIST" -d '\n' -P "$JOBS" -I{} bash -c 'compile_one "$@"' _ {}
 
 LIBOBJS=$(grep -v 'km_main\|km_cli\|km_utils\|/h_' "$LIST" | cut -d'|' -f2 | tr '\n' ' ')
-rm -f "$OUT/libkmref.a"; ar rcs "$OUT/libkmref.a" $LIBOBJS
-g++ -o "$OUT/bin/kmtricks" "$OBJ/km_main.o" "$OBJ/km_cli.o" "$OBJ/km_utils.o" "$OUT/libkmref.a" -lz -lpthread -ldl -export-dynamic
+rm -f "$OUT/libkmref$SUFFIX.a"; ar rcs "$OUT/libkmref$SUFFIX.a" $LIBOBJS
+g++ -o "$OUT/bin/kmtricks$SUFFIX" "$OBJ/km_main.o" "$OBJ/km_cli.o" "$OBJ/km_utils.o" "$OUT/libkmref$SUFFIX.a" -lz -lpthread -ldl -export-dynamic
+if [ -n "$SUFFIX" ]; then echo "oracle/_ref built: bin/kmtricks$SUFFIX ($MARCH)"; exit 0; fi
 for h in "$HERE"/ref_harness/*.cpp; do
   [ -e "$h" ] || continue
   b=$(basename "$h" .cpp)

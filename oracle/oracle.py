@@ -428,6 +428,19 @@ def run_pipeline(samples: list[list[bytes]], prm: Params):
 
 # ---------------------------------------------------------------------------- reference binary
 REF_BIN = os.path.join(_HERE, "_ref", "bin", "kmtricks")
+REF_BIN_V3 = os.path.join(_HERE, "_ref", "bin", "kmtricks_v3")   # -march=x86-64-v3 build of the same sources (timed baseline)
+
+
+def timed_ref_bin():
+    """(path, build note) of the reference binary to TIME on this host: the AVX2/BMI2/FMA build when the CPU has those
+    (what the reference's -DNATIVE=ON would use here), else the portable build.  Parity always uses REF_BIN."""
+    try:
+        flags = set(next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split())
+    except Exception:
+        flags = set()
+    if os.path.exists(REF_BIN_V3) and {"avx2", "bmi2", "fma", "movbe", "abm"} <= flags:
+        return REF_BIN_V3, "-O3 -march=x86-64-v3"
+    return REF_BIN, "-O3 (portable x86-64)"
 
 
 def have_ref() -> bool:

@@ -15,21 +15,24 @@ import torch
 import torch.distributed as dist
 
 
-def main():
+MODES = (("hash:bf:bin", dict(bloom_size=400_000, soft_min=2, share_min=2)), ("kmer:count:bin", {}),
+         ("kmer:pa:bin", dict(kmer_size=63, soft_min=2, recurrence_min=2)))
+
+
+def check(rank, world, local, n_local=3, P=8, reads=4000, modes=MODES, quiet=False):
+    """Runs the N-rank path on small seeded samples and compares every matrix, merge_info, counts file and .pinfo with
+    the CPU oracle (rank 0).  torch.distributed (nccl) must be initialised.  Returns True on every rank iff bit-identical."""
     from kmtricks_b200 import dist as kd, engine, formats, synth
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_local, P = 3, 8
+    P = max(P, world)
     ok = True
-    for mode, extra in (("hash:bf:bin", dict(bloom_size=400_000, soft_min=2, share_min=2)), ("kmer:count:bin", {}),
-                        ("kmer:pa:bin", dict(kmer_size=63, soft_min=2, recurrence_min=2))):
+    for mode, extra in modes:
+        extra = dict(extra)
         k = extra.pop("kmer_size", 31)
         cfg = engine.Config(kmer_size=k, nb_partitions=P, mode=mode, hard_min=2, **extra)
         N = world * n_local
         eng = engine.Engine(cfg, N, device=local)
         kd.init_engine(eng, nlanes=2)
-        texts = [synth.make_fastq(31, kd.global_slot(rank, n_local, i), 4000, L=150, G=30000, d=4e-3, e=4e-3, revcomp=True) for i in range(n_local)]
+        texts = [synth.make_fastq(31, kd.global_slot(rank, n_local, i), reads, L=150, G=30000, d=4e-3, e=4e-3, revcomp=True) for i in range(n_local)]
         bufs = [C.create_string_buffer(t, len(t)) for t in texts]
         ptrs = (C.c_void_p * n_local)(*[C.addressof(b) for b in bufs])
         sizes = (C.c_size_t * n_local)(*[len(t) for t in texts])
@@ -67,12 +70,21 @@ def main():
                             print(mode, "counts mismatch", s, p); ok = False
             if seen != set(range(P)):
                 print("partitions not covered", seen); ok = False
-            print(mode, "world", world, "OK" if ok else "FAIL", flush=True)
+            if not quiet:
+                print(mode, "world", world, "OK" if ok else "FAIL", flush=True)
         eng.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.broadcast(flag, src=0)
+    return int(flag.item()) == 0
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = check(rank, world, local)
     dist.destroy_process_group()
-    sys.exit(int(flag.item()))
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -20,5 +20,5 @@ $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT kmtricks_b200/_bui
 echo "built $OUT"
 # C++ host (CLI + run-dir + IMergePlugin host) over the C ABI
 mkdir -p kmtricks_b200/bin
-g++ -std=c++17 -O2 -Wall -Iinclude -o kmtricks_b200/bin/kmx kmtricks_b200/csrc/host/kmx_main.cpp -Lkmtricks_b200 -lkmx_sm100 -ldl -lz -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
+g++ -std=c++17 -O2 -Wall -Iinclude -o kmtricks_b200/bin/kmx kmtricks_b200/csrc/host/kmx_main.cpp -Lkmtricks_b200 -lkmx_sm100 -ldl -lz -lpthread -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
 echo "built kmtricks_b200/bin/kmx"

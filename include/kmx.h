@@ -94,6 +94,17 @@ int kmx_count_sample(kmx_ctx* ctx, uint32_t sample, uint32_t hard_min);
 int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* texts, const size_t* nbytes, int on_device,
                     const uint32_t* sample_ids, const uint32_t* hard_min, uint32_t nlanes,
                     uint64_t* kmers_per_partition);
+/* Lane-addressed variants for a host that STREAMS its inputs (what TaskScheduler does with one task per pool thread,
+ * task_scheduler.hpp:251-348): a lane is an independent in-flight sample (own CUDA stream, staging and buckets); one host
+ * thread drives one lane, several lanes run concurrently, so reading / inflating the next block of one sample overlaps the
+ * device work of the others and no input ever has to be resident as a whole.  kmx_lanes makes lanes 0..n-1 exist (n <= 8).
+ * A text block must be a whole number of FASTQ records and smaller than 4 GiB: push a large file in several blocks.     */
+int kmx_lanes(kmx_ctx* ctx, uint32_t n);
+int kmx_lane_superk_begin(kmx_ctx* ctx, uint32_t lane);
+int kmx_lane_superk_push_fastq(kmx_ctx* ctx, uint32_t lane, const char* text, size_t nbytes, int on_device);
+int kmx_lane_superk_push_reads(kmx_ctx* ctx, uint32_t lane, const char* seqs, const uint64_t* off, size_t nseq);
+int kmx_lane_superk_end(kmx_ctx* ctx, uint32_t lane, uint64_t* kmers_per_partition);
+int kmx_lane_count_sample(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min);
 /* size of / copy out one list == body of counts/partition_P/<id>.kmer|.hash
  * keys: n*w u64 (w = 1 for hash keys), counts: n u32.                                        */
 int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n);
@@ -151,6 +162,11 @@ int kmx_dist_init(kmx_ctx* ctx, int rank, int world, uint32_t nlanes, const uint
 int kmx_dist_owner(const kmx_ctx* ctx, uint32_t partition, int world);
 int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* const* texts, const size_t* nbytes, int on_device,
                          const uint32_t* hard_min, uint64_t* kmers_per_partition);
+/* The same for one BATCH of a longer run (inputs streamed batch by batch, or more samples than fit HBM as text): rank r's
+ * sample i of this batch lands in slot r*n_local_total + slot_base + i.  Every rank calls it with the same n, slot_base
+ * and n_local_total; an empty text (nbytes 0) is a valid sample (pads the last batch).                                   */
+int kmx_dist_run_batch(kmx_ctx* ctx, uint32_t n, const char* const* texts, const size_t* nbytes, int on_device,
+                       const uint32_t* hard_min, uint32_t slot_base, uint32_t n_local_total, uint64_t* kmers_per_partition);
 /* how many of the communicators' lanes kmx_dist_run_samples uses (1..nlanes of kmx_dist_init; every rank the same
  * value).  1 = samples strictly one after the other on one stream: the per-kernel profile spans are then exclusive.     */
 int kmx_dist_set_lanes(kmx_ctx* ctx, uint32_t nlanes);

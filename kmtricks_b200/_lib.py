@@ -48,6 +48,13 @@ SYMBOLS = {
     "kmx_dist_init": (_i, [_vp, _i, _i, _u32, _vp]),
     "kmx_dist_owner": (_i, [_vp, _u32, _i]),
     "kmx_dist_set_lanes": (_i, [_vp, _u32]),
+    "kmx_dist_run_batch": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), _u32, _u32, C.POINTER(_u64)]),
+    "kmx_lanes": (_i, [_vp, _u32]),
+    "kmx_lane_superk_begin": (_i, [_vp, _u32]),
+    "kmx_lane_superk_push_fastq": (_i, [_vp, _u32, _vp, _sz, _i]),
+    "kmx_lane_superk_push_reads": (_i, [_vp, _u32, _vp, _vp, _sz]),
+    "kmx_lane_superk_end": (_i, [_vp, _u32, C.POINTER(_u64)]),
+    "kmx_lane_count_sample": (_i, [_vp, _u32, _u32, _u32]),
     "kmx_dist_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u64)]),
     "kmx_counts_size": (_i, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "kmx_counts_get": (_i, [_vp, _u32, _u32, _vp, _vp]),

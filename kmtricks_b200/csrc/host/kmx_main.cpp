@@ -9,8 +9,16 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +45,8 @@ struct Options {
   uint64_t bloom = 10000000;
   bool keep_tmp = false, static_repart = true;
   int device = 0;
+  std::vector<int> devices;          // --devices a-b | a,b,c : partitions sharded over these GPUs (one in-process rank per GPU)
+  size_t block_mib = 256;            // FASTQ is streamed to the device in blocks of this many MiB (whole records)
   std::string key_kind, what, fmt;
 };
 
@@ -46,7 +56,7 @@ struct Options {
   std::cerr << "usage: kmx pipeline --file <fof> --run-dir <dir> --nb-partitions <P> [--kmer-size 31]\n"
                "           [--mode <kmer|hash>:<count|pa|bf|bft>:bin] [--hard-min 2] [--soft-min 1] [--recurrence-min 1]\n"
                "           [--share-min 0] [--minimizer-size 10] [--bloom-size 10000000] [--static-repart | --repart-from <run-dir>]\n"
-               "           [--until all|superk|count|merge] [--keep-tmp] [--threads 4] [--plugin lib.so [--plugin-config s]] [--device 0]\n";
+               "           [--until all|superk|count|merge] [--keep-tmp] [--threads 4] [--plugin lib.so [--plugin-config s]] [--device 0 | --devices 0-7] [--block-mib 256]\n";
   std::exit(why ? EXIT_FAILURE : EXIT_SUCCESS);
 }
 
@@ -76,6 +86,12 @@ Options parse(int argc, char** argv)
     else if (a == "--plugin") o.plugin = need(i);
     else if (a == "--plugin-config") o.plugin_config = need(i);
     else if (a == "--device") o.device = std::stoi(need(i));
+    else if (a == "--devices") {
+      std::string v = need(i); size_t d = v.find('-');
+      if (d != std::string::npos) { for (int g = std::stoi(v.substr(0, d)); g <= std::stoi(v.substr(d + 1)); g++) o.devices.push_back(g); }
+      else { std::stringstream ds(v); for (std::string t; std::getline(ds, t, ',');) o.devices.push_back(std::stoi(t)); }
+    }
+    else if (a == "--block-mib") o.block_mib = std::stoull(need(i));
     else if (a == "--help" || a == "-h") usage(nullptr);
     else usage(("unknown option " + a).c_str());
   }
@@ -86,6 +102,8 @@ Options parse(int argc, char** argv)
     usage("--mode must be <kmer|hash>:<count|pa|bf|bft>:bin");
   if ((o.what == "bf" || o.what == "bft") && o.key_kind != "hash") usage("bf/bft need hash keys");
   if (o.until != "all" && o.until != "superk" && o.until != "count" && o.until != "merge") usage("--until must be all|superk|count|merge");
+  if (o.devices.empty()) o.devices.push_back(o.device);
+  if (o.block_mib < 1 || o.block_mib > 3072) usage("--block-mib must be 1..3072 (a block must stay below 4 GiB)");
   return o;
 }
 
@@ -208,6 +226,53 @@ void parse_fastx(const std::string& b, std::string& seqs, std::vector<uint64_t>&
 
 #define KX(call) do { int rc_ = (call); if (rc_) throw Error(std::string(#call) + ": " + kmx_last_error(ctx)); } while (0)
 
+// ---------------------------------------------------------------------------- streaming FASTQ reader
+// Hands out a (possibly gzipped) strict 4-line FASTQ file in blocks of whole records: a block ends after the last newline
+// whose line number is a multiple of 4; the rest is carried into the next block.  Nothing but one block is ever resident.
+struct FastqBlocks {
+  gzFile f = nullptr; std::string carry; bool eof = false;
+  explicit FastqBlocks(const std::string& path) { f = gzopen(path.c_str(), "rb"); if (!f) throw Error("Unable to open " + path); gzbuffer(f, 1 << 20); }
+  ~FastqBlocks() { if (f) gzclose(f); }
+  // fills buf (cap bytes); returns the bytes of the block, 0 at the end of the file; throws when one record exceeds cap
+  size_t next(char* buf, size_t cap)
+  {
+    if (eof && carry.empty()) return 0;
+    size_t n = carry.size();
+    if (n > cap) throw Error("FASTQ record longer than a block (--block-mib)");
+    memcpy(buf, carry.data(), n); carry.clear();
+    while (!eof && n < cap) {
+      int r = gzread(f, buf + n, (unsigned)std::min<size_t>(cap - n, (size_t)1 << 30));
+      if (r < 0) throw Error("read error (gz)");
+      if (r == 0) eof = true; else n += (size_t)r;
+    }
+    if (eof) return n;                                   // the last block takes everything (a final line without '\n' included)
+    size_t lines = 0, cut = 0;
+    for (const char* p = buf; (p = (const char*)memchr(p, '\n', buf + n - p)) != nullptr; ) { p++; if (++lines % 4 == 0) cut = (size_t)(p - buf); }
+    if (cut == 0) throw Error("FASTQ record longer than a block (--block-mib)");
+    carry.assign(buf + cut, n - cut);
+    return cut;
+  }
+};
+
+// ---------------------------------------------------------------------------- writer thread (matrices are written while the next partition merges)
+struct WriteJob { std::string path, head; std::vector<uint8_t> body; };
+struct Writer {
+  std::mutex mu; std::condition_variable cv; std::deque<WriteJob> q; bool stop = false; std::exception_ptr err; std::thread th;
+  Writer() : th([this] { run(); }) {}
+  void run()
+  {
+    for (;;) {
+      WriteJob j;
+      { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return stop || !q.empty(); }); if (q.empty()) return; j = std::move(q.front()); q.pop_front(); }
+      cv.notify_all();
+      try { write_file(j.path, j.head, j.body.data(), j.body.size()); } catch (...) { std::lock_guard<std::mutex> l(mu); if (!err) err = std::current_exception(); }
+    }
+  }
+  void push(WriteJob&& j) { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return q.size() < 2; }); q.push_back(std::move(j)); cv.notify_all(); }
+  void finish() { { std::lock_guard<std::mutex> l(mu); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); if (err) std::rethrow_exception(err); }
+  ~Writer() { try { finish(); } catch (...) {} }
+};
+
 // ---------------------------------------------------------------------------- plugin host
 struct PluginHost {
   void* handle = nullptr;
@@ -231,12 +296,199 @@ struct PluginHost {
   ~PluginHost() { if (handle) dlclose(handle); }
 };
 
+// HowDeSBT Bloom filter file header of a simple uncompressed one-vector filter, as howde_utils.hpp:57-90 fills it.  The struct
+// (bloom_filter_file.h of HowDeSBT) is NOT vendored in the reference: field order and magic numbers below are restated from
+// HowDeSBT's published header -- parity UNPINNED (the reference cannot build one at this commit); the payload placement is pinned.
+static const size_t HOWDE_HEADER_BYTES = 112;           // round_up_16(sizeof(bffileheader) with one bfvectorinfo) = 0x50 + 0x20
+std::string howde_header(uint32_t k, uint64_t bloom_bits)
+{
+  std::string h(HOWDE_HEADER_BYTES, '\0');
+  auto w32 = [&](size_t o, uint32_t v) { memcpy(&h[o], &v, 4); };
+  auto w64 = [&](size_t o, uint64_t v) { memcpy(&h[o], &v, 8); };
+  w64(0x00, 0xD532006662544253ULL);                      // bffileheaderMagic ("SBTbf")
+  w32(0x08, (uint32_t)HOWDE_HEADER_BYTES); w32(0x0C, 1); // headerSize, version
+  w32(0x10, 1);                                          // bfKind = bfkind_simple
+  w32(0x18, k); w32(0x1C, 1);                            // smerSize, numHashes
+  w64(0x20, 0); w64(0x28, 0);                            // hashSeed1, hashSeed2
+  w64(0x30, bloom_bits); w64(0x38, bloom_bits);          // hashModulus, numBits
+  w32(0x40, 1); w32(0x44, 0); w64(0x48, 0);              // numVectors, setSizeKnown, setSize
+  w32(0x50, 1); w32(0x54, 0);                            // info[0].compressor = bvcomp_uncompressed, name
+  w64(0x58, HOWDE_HEADER_BYTES);                         // info[0].offset
+  w64(0x60, bloom_bits / 8 + 8); w64(0x68, 0);           // info[0].numBytes (sdsl bit_vector: u64 bit count + words), filterInfo
+  return h;
+}
+
+// ---------------------------------------------------------------------------- one GPU (one rank)
+struct Rank {
+  int device = 0; kmx_ctx* ctx = nullptr;
+  uint32_t first_part = 0, last_part = 0;                // owned partitions [first, last)
+};
+
+struct Run {
+  Options o; std::vector<Sample> samples; uint32_t N = 0, P = 0, w = 1; bool hash = false; uint64_t W = 0;
+  std::vector<std::vector<uint64_t>> pinfo;
+  std::mutex err_mu; std::exception_ptr err; std::atomic<bool> failed{false};
+  void fail(std::exception_ptr e) { std::lock_guard<std::mutex> l(err_mu); if (!err) err = e; failed = true; }
+  uint32_t hard_min(uint32_t s) const { return samples[s].hard_min ? samples[s].hard_min : o.hard_min; }
+};
+
+// kseq-parsed whole file(s): FASTA, multi-line records, anything that is not strict 4-line FASTQ
+void push_parsed(kmx_ctx* ctx, uint32_t lane, const std::string& path)
+{
+  std::string text = read_all(path);
+  int rc = (!text.empty() && text[0] == '@' && text.size() < 0xFFFFFFF0ULL) ? kmx_lane_superk_push_fastq(ctx, lane, text.data(), text.size(), 0) : KMX_ERR_FORMAT;
+  if (rc == KMX_ERR_FORMAT) {
+    std::string seqs; std::vector<uint64_t> off; parse_fastx(text, seqs, off);
+    text.clear(); text.shrink_to_fit();
+    KX(kmx_lane_superk_push_reads(ctx, lane, seqs.data(), off.data(), off.size() - 1));
+  } else if (rc) throw Error(std::string("kmx_lane_superk_push_fastq: ") + kmx_last_error(ctx));
+}
+
+// stage 1 + 2 of one sample on one lane, its files streamed block by block through the lane's pinned buffer
+void process_sample(Run& R, kmx_ctx* ctx, uint32_t lane, uint32_t s, char* pin, size_t pin_cap)
+{
+  const Sample& smp = R.samples[s];
+  bool streamed = true;
+  KX(kmx_lane_superk_begin(ctx, lane));
+  for (const std::string& f : smp.files) {
+    FastqBlocks fb(f);
+    bool first = true;
+    for (size_t n; streamed && (n = fb.next(pin, pin_cap)) != 0; first = false) {
+      if (first && pin[0] != '@') { streamed = false; break; }
+      int rc = kmx_lane_superk_push_fastq(ctx, lane, pin, n, 0);
+      if (rc == KMX_ERR_FORMAT) streamed = false;          // multi-line FASTQ, ...: the host parses it kseq-style
+      else if (rc) throw Error(std::string("kmx_lane_superk_push_fastq: ") + kmx_last_error(ctx));
+    }
+    if (!streamed) break;
+  }
+  if (!streamed) {                                         // restart the sample (begin clears what the blocks had put into the buckets)
+    KX(kmx_lane_superk_begin(ctx, lane));
+    for (const std::string& f : smp.files) push_parsed(ctx, lane, f);
+  }
+  KX(kmx_lane_superk_end(ctx, lane, R.pinfo[s].data()));
+  if (R.o.until != "superk") KX(kmx_lane_count_sample(ctx, lane, s, R.hard_min(s)));
+}
+
+std::string matrix_header(const Run& R, uint32_t p)
+{
+  const Options& o = R.o; const uint32_t N = R.N, w = R.w, nbytes = (N + 7) / 8;
+  std::string h = km_header();
+  if (!R.hash && o.what == "count") { put<uint64_t>(h, 0x6b5f78697274616dULL); put<uint32_t>(h, o.k); put<uint32_t>(h, w); put<uint32_t>(h, 1); put<uint32_t>(h, N); put<uint32_t>(h, 0); put<uint32_t>(h, 0); }
+  else if (!R.hash) { put<uint64_t>(h, 0x6b5f74616d6170ULL); put<uint32_t>(h, o.k); put<uint32_t>(h, w); put<uint32_t>(h, N); put<uint32_t>(h, nbytes); put<uint32_t>(h, 0); put<uint32_t>(h, 0); }
+  else if (o.what == "count") { put<uint64_t>(h, 0x685f78697274616dULL); put<uint32_t>(h, 4); put<uint32_t>(h, N); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
+  else if (o.what == "pa") { put<uint64_t>(h, 0x685f74616d6170ULL); put<uint32_t>(h, N); put<uint32_t>(h, nbytes); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
+  else { put<uint64_t>(h, 0x74616d746962ULL); put<uint32_t>(h, N); put<uint64_t>(h, R.W * p); put<uint64_t>(h, R.W); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
+  return h;
+}
+
+// counts/partition_P/<id>.kmer|.hash of the partitions this rank holds (kmer_file.hpp:31-108, hash_file.hpp:31-131)
+void write_counts(const Run& R, const Rank& rk)
+{
+  kmx_ctx* ctx = rk.ctx; const Options& o = R.o;
+  for (uint32_t s = 0; s < R.N; s++) for (uint32_t p = rk.first_part; p < rk.last_part; p++) {
+    uint64_t n = 0; KX(kmx_counts_size(ctx, s, p, &n));
+    const uint32_t kw = R.hash ? 1 : R.w;
+    std::vector<uint64_t> keys(n * kw); std::vector<uint32_t> cnt(n);
+    KX(kmx_counts_get(ctx, s, p, keys.data(), cnt.data()));
+    std::string path = o.dir + "/counts/partition_" + std::to_string(p) + "/" + R.samples[s].id + (R.hash ? ".hash" : ".kmer");
+    std::string h = km_header(), body;
+    if (!R.hash) {
+      put<uint64_t>(h, 0x72656d6bULL); put<uint32_t>(h, o.k); put<uint32_t>(h, R.w); put<uint32_t>(h, 4); put<uint32_t>(h, s); put<uint32_t>(h, p);
+      body.reserve(n * (8 * R.w + 4));
+      for (uint64_t i = 0; i < n; i++) { body.append((const char*)&keys[i * R.w], 8 * R.w); body.append((const char*)&cnt[i], 4); }
+    } else {
+      put<uint64_t>(h, 0x68736168ULL); put<uint32_t>(h, 4); put<uint32_t>(h, s); put<uint32_t>(h, p);
+      for (uint64_t i = 0; i < n; i += 4096) {
+        uint64_t b = std::min<uint64_t>(4096, n - i);
+        put<uint64_t>(body, b); body.append((const char*)&keys[i], 8 * b); body.append((const char*)&cnt[i], 4 * b);
+      }
+    }
+    write_file(path, h, body.data(), body.size());
+  }
+}
+
+// merge of the partitions this rank owns (KmerMergeTask / HashMergeTask, task.hpp:690-870); files go through the writer thread
+void merge_partitions(Run& R, const Rank& rk, PluginHost& plug, const std::vector<int>& bf_fds)
+{
+  kmx_ctx* ctx = rk.ctx; const Options& o = R.o; const uint32_t N = R.N, w = R.w; const bool hash = R.hash; const uint64_t W = R.W;
+  std::vector<uint32_t> soft(N, o.soft_min);
+  const char* ext = !hash ? (o.what == "count" ? "count" : "pa") : (o.what == "count" ? "count_hash" : o.what == "pa" ? "pa_hash" : "cmbf");
+  const uint32_t nbytes = (N + 7) / 8, kw = hash ? 1 : w;
+  const uint32_t fmt = o.what == "count" ? KMX_FMT_COUNT : o.what == "pa" ? KMX_FMT_PA : o.what == "bf" ? KMX_FMT_BF : KMX_FMT_BFT;
+  Writer writer;
+  for (uint32_t p = rk.first_part; p < rk.last_part && !R.failed; p++) {
+    // with a plugin every merged row goes through it, whatever the output mode (merge.hpp:249-257,509-514): the library
+    // returns all rows with their counts, the plugin decides / edits, and the host encodes the mode's row from its counts
+    kmx_merge_params mp{soft.data(), o.rec_min, o.share_min, plug.handle ? (uint32_t)KMX_FMT_COUNT : fmt, (uint32_t)(plug.handle ? 1 : 0)};
+    kmx_merge_result r{};
+    KX(kmx_merge_partition(ctx, p, &mp, &r));
+    WriteJob job; job.path = o.dir + "/matrices/matrix_" + std::to_string(p) + "." + ext; job.head = matrix_header(R, p);
+    std::vector<uint8_t> body(r.n_rows * r.row_bytes), keep(plug.handle ? r.n_rows : 0);
+    std::vector<uint64_t> stats((size_t)6 * N);
+    KX(kmx_merge_get(ctx, body.data(), stats.data(), plug.handle ? keep.data() : nullptr));
+    if (!plug.handle) job.body = std::move(body);
+    else {
+      // one plugin instance per merge task (task.hpp:701-712), called once per merged row in key order;
+      // its return value replaces the keep decision and it may edit the counts
+      km::IMergePlugin* pl = plug.create();
+      pl->configure(plug.config);
+      pl->set_out_dir(o.dir + "/plugin_output");
+      pl->set_kmer_size(hash ? 0 : o.k);
+      pl->set_partition(p);
+      std::vector<uint32_t> c(N);
+      std::vector<uint8_t>& out = job.body;
+      const bool dense = fmt == KMX_FMT_BF || fmt == KMX_FMT_BFT;
+      if (dense) out.assign((size_t)W * nbytes, 0);
+      for (uint64_t i = 0; i < r.n_rows; i++) {
+        const uint8_t* row = &body[i * r.row_bytes];
+        memcpy(c.data(), row + 8 * kw, 4 * N);
+        uint64_t kbuf[2]; memcpy(kbuf, row, 8 * kw);
+        const bool kp = hash ? pl->process_hash(kbuf[0], c) : pl->process_kmer(kbuf, c);
+        if (!kp) continue;
+        if (fmt == KMX_FMT_COUNT) { out.insert(out.end(), (const uint8_t*)kbuf, (const uint8_t*)kbuf + 8 * kw); out.insert(out.end(), (const uint8_t*)c.data(), (const uint8_t*)c.data() + 4 * N); }
+        else {
+          uint8_t* bits;
+          if (dense) bits = &out[(size_t)(kbuf[0] - W * p) * nbytes];
+          else { const size_t at = out.size(); out.resize(at + 8 * kw + nbytes, 0); memcpy(&out[at], kbuf, 8 * kw); bits = &out[at + 8 * kw]; }
+          for (uint32_t s2 = 0; s2 < N; s2++) if (c[s2]) bits[s2 >> 3] |= (uint8_t)(1u << (s2 & 7));
+        }
+      }
+      plug.destroy(pl);
+      if (fmt == KMX_FMT_BFT) {                            // W x 8*nbytes bits -> 8*nbytes x W bits (BitMatrix::transpose) on the device
+        std::vector<uint8_t> t(out.size());
+        KX(kmx_transpose_bits(ctx, out.data(), W, (uint64_t)nbytes * 8, t.data()));
+        out.swap(t);
+      }
+    }
+    if (fmt == KMX_FMT_BFT && !bf_fds.empty()) {           // per-sample filter: row s of this partition at its place in filters/<id>.bf
+      const size_t rb = W / 8;
+      for (uint32_t s2 = 0; s2 < N; s2++)
+        if (pwrite(bf_fds[s2], &job.body[(size_t)s2 * rb], rb, (off_t)(HOWDE_HEADER_BYTES + 8 + (uint64_t)p * rb)) != (ssize_t)rb) throw Error("Unable to write filters/" + R.samples[s2].id + ".bf");
+    }
+    writer.push(std::move(job));
+    {   // merge_infos/partitionP.merge_info (merge.hpp:72-83)
+      static const char* names[6] = {"NON_SOLID", "RESCUED", "UNIQUE_WO_RESCUE", "UNIQUE_W_RESCUE", "TOTAL_WO_RESCUE", "TOTAL_W_RESCUE"};
+      std::ofstream mi(o.dir + "/merge_infos/partition" + std::to_string(p) + ".merge_info");
+      for (int q = 0; q < 6; q++) { mi << names[q] << '\t'; for (uint32_t s2 = 0; s2 < N; s2++) mi << stats[(size_t)q * N + s2] << '\t'; mi << "\n"; }
+    }
+    if (o.what == "bf") {   // fpr/partition_P.txt (task.hpp:849-860; utils.hpp:239-243) -- the only floating point on the path
+      std::ofstream fp(o.dir + "/fpr/partition_" + std::to_string(p) + ".txt");
+      for (uint32_t s2 = 0; s2 < N; s2++) {
+        double nn = (double)stats[(size_t)3 * N + s2];
+        double fpr = std::pow(1.0 - std::pow(std::exp(1.0), (-(1.0 * nn)) / (double)W), 1.0);
+        fp << std::fixed << fpr << "\n";
+      }
+    }
+  }
+  writer.finish();
+}
+
 }  // namespace
 
 int main(int argc, char** argv)
 {
   const auto t0 = std::chrono::steady_clock::now();
-  kmx_ctx* ctx = nullptr;
+  std::vector<Rank> ranks;
   try {
     if (argc == 3 && std::string(argv[1]) == "fof") {     // host-side check, no device: prints the parsed input list
       for (const Sample& s : read_fof(argv[2])) {
@@ -246,11 +498,16 @@ int main(int argc, char** argv)
       }
       return EXIT_SUCCESS;
     }
-    Options o = parse(argc, argv);
-    std::vector<Sample> samples = read_fof(o.fof);
-    const uint32_t N = (uint32_t)samples.size(), P = o.P, w = (o.k + 31) / 32;
-    const bool hash = o.key_kind == "hash";
-    const uint64_t W = window_bits(o.bloom, P);
+    Run R;
+    R.o = parse(argc, argv);
+    const Options& o = R.o;
+    R.samples = read_fof(o.fof);
+    const uint32_t N = R.N = (uint32_t)R.samples.size(), P = R.P = o.P; R.w = (o.k + 31) / 32;
+    const bool hash = R.hash = o.key_kind == "hash";
+    const uint64_t W = R.W = window_bits(o.bloom, P);
+    const int G = (int)o.devices.size();
+    if (G > 1 && (uint32_t)G > P) throw Error("--devices: more GPUs than partitions");
+    R.pinfo.assign(N, std::vector<uint64_t>(P, 0));
     // ---- run directory (kmdir.hpp:195-236)
     for (const char* d : {"", "/config_gatb", "/repartition_gatb", "/superkmers", "/counts", "/matrices", "/merge_infos",
                           "/partition_infos", "/fpr", "/plugin_output", "/histograms", "/minimizers", "/filters", "/howde_index"})
@@ -263,7 +520,7 @@ int main(int argc, char** argv)
          << ", m_ab_min=" << o.soft_min << ", r_min=" << o.rec_min << ", save_if=" << o.share_min << ", minim_size=" << o.m << ", nb_parts=" << P
          << ", bloom_size=" << o.bloom << ", keep_tmp=" << o.keep_tmp << ", static_repart=" << o.static_repart << ", use_plugin=" << !o.plugin.empty()
          << ", plugin=" << o.plugin << ", plugin_config=" << o.plugin_config << ", mode=" << o.what << ", format=bin, count_format=" << o.key_kind
-         << ", until=" << o.until << ", engine=kmx_sm100\n";
+         << ", until=" << o.until << ", engine=kmx_sm100, gpus=" << G << "\n";
     }
     { std::string h; put<uint64_t>(h, W * P); put<uint64_t>(h, P); put<uint64_t>(h, W); put<uint64_t>(h, W / 8); put<uint32_t>(h, o.m); write_file(o.dir + "/hash.info", h, nullptr, 0); }
     // ---- repartition table (RepartTask, task.hpp:170-222)
@@ -286,140 +543,112 @@ int main(int argc, char** argv)
     kmx_params prm{};
     prm.kmer_size = o.k; prm.minim_size = o.m; prm.nb_partitions = P; prm.key_kind = hash ? KMX_KEY_HASH : KMX_KEY_KMER;
     prm.window_bits = hash ? W : 0; prm.repart_table = table.data(); prm.nb_samples = N;
-    if (int rc = kmx_create(o.device, &prm, &ctx)) throw Error(std::string("kmx_create: ") + (ctx ? kmx_last_error(ctx) : "failed") + " (code " + std::to_string(rc) + ")");
+    ranks.resize(G);
+    for (int g = 0; g < G; g++) {
+      ranks[g].device = o.devices[g];
+      ranks[g].first_part = (uint32_t)(((uint64_t)g * P) / G); ranks[g].last_part = (uint32_t)(((uint64_t)(g + 1) * P) / G);
+      if (int rc = kmx_create(o.devices[g], &prm, &ranks[g].ctx))
+        throw Error(std::string("kmx_create: ") + (ranks[g].ctx ? kmx_last_error(ranks[g].ctx) : "failed") + " (code " + std::to_string(rc) + ")");
+    }
+    const uint32_t lanes = std::max(1u, std::min(o.threads, 8u));        // --threads = samples in flight per GPU
 
     // ---- superk + count (TaskScheduler::exec_superk_count, task_scheduler.hpp:251-348)
-    // fast path: every sample is one plain strict FASTQ file -> kmx_run_samples over pinned buffers
-    std::vector<std::vector<uint64_t>> pinfo(N, std::vector<uint64_t>(P, 0));
-    std::vector<std::string> texts(N);
-    bool all_fastq = true;
-    for (uint32_t s = 0; s < N; s++) {
-      if (samples[s].files.size() != 1) { all_fastq = false; break; }
-      texts[s] = read_all(samples[s].files[0]);
-      if (texts[s].empty() || texts[s][0] != '@') { all_fastq = false; break; }
-    }
-    bool done = false;
-    if (all_fastq && o.until != "superk") {
-      std::vector<const char*> ptr(N); std::vector<size_t> nb(N); std::vector<uint32_t> hm(N); std::vector<uint64_t> flat((size_t)N * P);
-      for (uint32_t s = 0; s < N; s++) { ptr[s] = texts[s].data(); nb[s] = texts[s].size(); hm[s] = samples[s].hard_min ? samples[s].hard_min : o.hard_min; }
-      int rc = kmx_run_samples(ctx, N, ptr.data(), nb.data(), 0, nullptr, hm.data(), std::max(1u, std::min(o.threads, 8u)), flat.data());
-      if (rc == KMX_OK) { for (uint32_t s = 0; s < N; s++) std::copy(flat.begin() + (size_t)s * P, flat.begin() + (size_t)(s + 1) * P, pinfo[s].begin()); done = true; }
-      else if (rc != KMX_ERR_FORMAT) throw Error(std::string("kmx_run_samples: ") + kmx_last_error(ctx));
-      else KX(kmx_reset(ctx));
-    }
-    if (!done) {
-      for (uint32_t s = 0; s < N; s++) {
-        KX(kmx_superk_begin(ctx));
-        for (const std::string& f : samples[s].files) {
-          std::string text = read_all(f);
-          int rc = (!text.empty() && text[0] == '@') ? kmx_superk_push_fastq(ctx, text.data(), text.size(), 0) : KMX_ERR_FORMAT;
-          if (rc == KMX_ERR_FORMAT) {
-            std::string seqs; std::vector<uint64_t> off; parse_fastx(text, seqs, off);
-            KX(kmx_superk_push_reads(ctx, seqs.data(), off.data(), off.size() - 1));
-          } else if (rc) throw Error(std::string("kmx_superk_push_fastq: ") + kmx_last_error(ctx));
-        }
-        KX(kmx_superk_end(ctx, pinfo[s].data()));
-        if (o.until != "superk") KX(kmx_count_sample(ctx, s, samples[s].hard_min ? samples[s].hard_min : o.hard_min));
-      }
+    if (G == 1) {
+      // one host thread per lane: it reads / inflates a block of its sample into its pinned buffer and pushes it, while the
+      // other lanes' blocks are on the device -- no input is ever resident as a whole, a block is < 4 GiB by construction
+      kmx_ctx* ctx = ranks[0].ctx;
+      const uint32_t T = std::min<uint32_t>(lanes, std::max(1u, N));
+      KX(kmx_lanes(ctx, T));
+      std::atomic<uint32_t> next{0};
+      auto work = [&](uint32_t t) {
+        void* pin = nullptr; const size_t cap = o.block_mib << 20;
+        try {
+          if (kmx_host_alloc(cap, &pin)) throw Error("pinned block buffer: out of memory");
+          for (uint32_t s; !R.failed && (s = next.fetch_add(1)) < N;) process_sample(R, ctx, t, s, (char*)pin, cap);
+        } catch (...) { R.fail(std::current_exception()); }
+        if (pin) kmx_host_free(pin);
+      };
+      std::vector<std::thread> th;
+      for (uint32_t t = 0; t < T; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+      if (R.err) std::rethrow_exception(R.err);
+      KX(kmx_sync(ctx));
+    } else {
+      // one in-process rank per GPU: rank g parses the samples [g nl, (g+1) nl), the buckets travel to the partitions' owners
+      // (one NCCL all-to-all-v per sample), every rank counts and later merges its own partitions.  Batches of a few samples.
+      if (o.until == "superk") throw Error("--until superk needs a single --device");
+      const uint32_t nl = (N + G - 1) / G, B = std::max(lanes, 4u);
+      std::vector<uint8_t> ids((size_t)128 * lanes);
+      for (uint32_t t = 0; t < lanes; t++) if (kmx_dist_unique_id(&ids[(size_t)128 * t])) throw Error("kmx_dist_unique_id failed (libnccl.so.2 not loadable?)");
+      auto work = [&](int g) {
+        kmx_ctx* ctx = ranks[g].ctx;
+        try {
+          KX(kmx_dist_init(ctx, g, G, lanes, ids.data()));
+          for (uint32_t b0 = 0; b0 < nl; b0 += B) {
+            const uint32_t nb = std::min(B, nl - b0);
+            std::vector<std::string> texts(nb); std::vector<const char*> ptr(nb); std::vector<size_t> sz(nb); std::vector<uint32_t> hm(nb, o.hard_min);
+            std::vector<uint64_t> flat((size_t)nb * P);
+            for (uint32_t i = 0; i < nb; i++) {
+              const uint64_t s = (uint64_t)g * nl + b0 + i;
+              if (s < N) {
+                if (R.samples[s].files.size() != 1) throw Error("--devices: one strict 4-line FASTQ file per sample");
+                texts[i] = read_all(R.samples[s].files[0]); hm[i] = R.hard_min((uint32_t)s);
+                if (texts[i].size() >= 0xFFFFFFF0ULL) throw Error("--devices: sample files must be < 4 GiB uncompressed");
+              }
+              ptr[i] = texts[i].data(); sz[i] = texts[i].size();
+            }
+            // every rank makes the same sequence of calls, also when one of them has failed: the library reports a failed peer
+            int rc = kmx_dist_run_batch(ctx, nb, ptr.data(), sz.data(), 0, hm.data(), b0, nl, flat.data());
+            if (rc) throw Error(std::string("kmx_dist_run_batch: ") + kmx_last_error(ctx));
+            for (uint32_t i = 0; i < nb; i++) { const uint64_t s = (uint64_t)g * nl + b0 + i; if (s < N) std::copy(flat.begin() + (size_t)i * P, flat.begin() + (size_t)(i + 1) * P, R.pinfo[s].begin()); }
+          }
+          KX(kmx_sync(ctx));
+        } catch (...) { R.fail(std::current_exception()); }
+      };
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; g++) th.emplace_back(work, g);
+      for (auto& x : th) x.join();
+      if (R.err) std::rethrow_exception(R.err);
     }
     for (uint32_t s = 0; s < N; s++) {        // partition_infos/<id>.pinfo (gatb_utils.hpp:46-51)
-      std::ofstream pi(o.dir + "/partition_infos/" + samples[s].id + ".pinfo");
-      for (uint32_t p = 0; p < P; p++) pi << pinfo[s][p] << "\n";
+      std::ofstream pi(o.dir + "/partition_infos/" + R.samples[s].id + ".pinfo");
+      for (uint32_t p = 0; p < P; p++) pi << R.pinfo[s][p] << "\n";
     }
-    // ---- counts/ files (kept with --keep-tmp or when stopping at count: kmer_file.hpp:31-108, hash_file.hpp:31-131)
-    if (o.until != "superk" && (o.keep_tmp || o.until == "count")) {
-      for (uint32_t s = 0; s < N; s++) for (uint32_t p = 0; p < P; p++) {
-        uint64_t n = 0; KX(kmx_counts_size(ctx, s, p, &n));
-        const uint32_t kw = hash ? 1 : w;
-        std::vector<uint64_t> keys(n * kw); std::vector<uint32_t> cnt(n);
-        KX(kmx_counts_get(ctx, s, p, keys.data(), cnt.data()));
-        std::string path = o.dir + "/counts/partition_" + std::to_string(p) + "/" + samples[s].id + (hash ? ".hash" : ".kmer");
-        std::string h = km_header();
-        std::string body;
-        if (!hash) {
-          put<uint64_t>(h, 0x72656d6bULL); put<uint32_t>(h, o.k); put<uint32_t>(h, w); put<uint32_t>(h, 4); put<uint32_t>(h, s); put<uint32_t>(h, p);
-          body.reserve(n * (8 * w + 4));
-          for (uint64_t i = 0; i < n; i++) { body.append((const char*)&keys[i * w], 8 * w); body.append((const char*)&cnt[i], 4); }
-        } else {
-          put<uint64_t>(h, 0x68736168ULL); put<uint32_t>(h, 4); put<uint32_t>(h, s); put<uint32_t>(h, p);
-          for (uint64_t i = 0; i < n; i += 4096) {
-            uint64_t b = std::min<uint64_t>(4096, n - i);
-            put<uint64_t>(body, b); body.append((const char*)&keys[i], 8 * b); body.append((const char*)&cnt[i], 4 * b);
-          }
-        }
-        write_file(path, h, body.data(), body.size());
-      }
-    }
-    // ---- merge (KmerMergeTask / HashMergeTask, task.hpp:690-870)
+    // ---- counts/ files (kept with --keep-tmp or when stopping at count)
+    if (o.until != "superk" && (o.keep_tmp || o.until == "count")) for (const Rank& rk : ranks) write_counts(R, rk);
+    // ---- merge: every rank its own partitions, concurrently
     if (o.until == "all" || o.until == "merge") {
       PluginHost plug;
-      if (!o.plugin.empty()) { if (o.what != "count") throw Error("--plugin needs a count matrix mode"); plug.load(o.plugin, o.plugin_config, o.k); }
-      std::vector<uint32_t> soft(N, o.soft_min);
-      const char* ext = !hash ? (o.what == "count" ? "count" : "pa") : (o.what == "count" ? "count_hash" : o.what == "pa" ? "pa_hash" : "cmbf");
-      const uint32_t nbytes = (N + 7) / 8;
-      for (uint32_t p = 0; p < P; p++) {
-        kmx_merge_params mp{soft.data(), o.rec_min, o.share_min,
-                            (uint32_t)(o.what == "count" ? KMX_FMT_COUNT : o.what == "pa" ? KMX_FMT_PA : o.what == "bf" ? KMX_FMT_BF : KMX_FMT_BFT),
-                            (uint32_t)(plug.handle ? 1 : 0)};
-        kmx_merge_result r{};
-        KX(kmx_merge_partition(ctx, p, &mp, &r));
-        std::vector<uint8_t> body(r.n_rows * r.row_bytes), keep(plug.handle ? r.n_rows : 0);
-        std::vector<uint64_t> stats((size_t)6 * N);
-        KX(kmx_merge_get(ctx, body.data(), stats.data(), plug.handle ? keep.data() : nullptr));
-        std::string h = km_header();
-        if (!hash && o.what == "count") { put<uint64_t>(h, 0x6b5f78697274616dULL); put<uint32_t>(h, o.k); put<uint32_t>(h, w); put<uint32_t>(h, 1); put<uint32_t>(h, N); put<uint32_t>(h, 0); put<uint32_t>(h, 0); }
-        else if (!hash) { put<uint64_t>(h, 0x6b5f74616d6170ULL); put<uint32_t>(h, o.k); put<uint32_t>(h, w); put<uint32_t>(h, N); put<uint32_t>(h, nbytes); put<uint32_t>(h, 0); put<uint32_t>(h, 0); }
-        else if (o.what == "count") { put<uint64_t>(h, 0x685f78697274616dULL); put<uint32_t>(h, 4); put<uint32_t>(h, N); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
-        else if (o.what == "pa") { put<uint64_t>(h, 0x685f74616d6170ULL); put<uint32_t>(h, N); put<uint32_t>(h, nbytes); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
-        else { put<uint64_t>(h, 0x74616d746962ULL); put<uint32_t>(h, N); put<uint64_t>(h, W * p); put<uint64_t>(h, W); put<uint32_t>(h, 0); put<uint32_t>(h, p); }
-        const std::string mpath = o.dir + "/matrices/matrix_" + std::to_string(p) + "." + ext;
-        if (!plug.handle) write_file(mpath, h, body.data(), body.size());
-        else {
-          // one plugin instance per merge task (task.hpp:701-712), called once per merged row in key order;
-          // its return value replaces the keep decision and it may edit the counts (merge.hpp:249-257)
-          km::IMergePlugin* pl = plug.create();
-          pl->configure(plug.config);
-          pl->set_out_dir(o.dir + "/plugin_output");
-          pl->set_kmer_size(hash ? 0 : o.k);
-          pl->set_partition(p);
-          const uint32_t kw = hash ? 1 : w;
-          std::string out; std::vector<uint32_t> c(N);
-          for (uint64_t i = 0; i < r.n_rows; i++) {
-            const uint8_t* row = &body[i * r.row_bytes];
-            memcpy(c.data(), row + 8 * kw, 4 * N);
-            const uint64_t* key = reinterpret_cast<const uint64_t*>(row);
-            uint64_t kbuf[2]; memcpy(kbuf, key, 8 * kw);
-            bool kp = hash ? pl->process_hash(kbuf[0], c) : pl->process_kmer(kbuf, c);
-            if (kp) { out.append((const char*)kbuf, 8 * kw); out.append((const char*)c.data(), 4 * N); }
-          }
-          plug.destroy(pl);
-          write_file(mpath, h, out.data(), out.size());
-        }
-        {   // merge_infos/partitionP.merge_info (merge.hpp:72-83)
-          static const char* names[6] = {"NON_SOLID", "RESCUED", "UNIQUE_WO_RESCUE", "UNIQUE_W_RESCUE", "TOTAL_WO_RESCUE", "TOTAL_W_RESCUE"};
-          std::ofstream mi(o.dir + "/merge_infos/partition" + std::to_string(p) + ".merge_info");
-          for (int q = 0; q < 6; q++) { mi << names[q] << '\t'; for (uint32_t s = 0; s < N; s++) mi << stats[(size_t)q * N + s] << '\t'; mi << "\n"; }
-        }
-        if (o.what == "bf") {   // fpr/partition_P.txt (task.hpp:849-860; utils.hpp:239-243) -- the only floating point on the path
-          std::ofstream fp(o.dir + "/fpr/partition_" + std::to_string(p) + ".txt");
-          for (uint32_t s = 0; s < N; s++) {
-            double nn = (double)stats[(size_t)3 * N + s];
-            double fpr = std::pow(1.0 - std::pow(std::exp(1.0), (-(1.0 * nn)) / (double)W), 1.0);
-            fp << std::fixed << fpr << "\n";
-          }
+      if (!o.plugin.empty()) plug.load(o.plugin, o.plugin_config, o.k);
+      std::vector<int> bf_fds;
+      if (o.what == "bft") {                               // filters/<id>.bf: HowDeSBT header, u64 number of bits, then the partitions' rows
+        const std::string hd = howde_header(o.k, W * P);
+        const uint64_t bits = W * P;
+        for (uint32_t s = 0; s < N; s++) {
+          const std::string path = o.dir + "/filters/" + R.samples[s].id + ".bf";
+          int fd = open(path.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644);
+          if (fd < 0) throw Error("Unable to write at " + path);
+          if (pwrite(fd, hd.data(), hd.size(), 0) != (ssize_t)hd.size() || pwrite(fd, &bits, 8, HOWDE_HEADER_BYTES) != 8) throw Error("Unable to write at " + path);
+          bf_fds.push_back(fd);
         }
       }
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; g++) th.emplace_back([&, g] { try { merge_partitions(R, ranks[g], plug, bf_fds); } catch (...) { R.fail(std::current_exception()); } });
+      for (auto& x : th) x.join();
+      for (int fd : bf_fds) close(fd);
+      if (R.err) std::rethrow_exception(R.err);
     }
     {
       double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      uint64_t launches = 0; for (const Rank& rk : ranks) launches += kmx_launch_count(rk.ctx);
       std::ofstream ri(o.dir + "/run_infos.txt");
-      ri << "Time: " << (long)sec << " seconds\n" << "GPU kernels launched: " << kmx_launch_count(ctx) << "\n";
+      ri << "Time: " << (long)sec << " seconds\n" << "GPU kernels launched: " << launches << "\n";
     }
-    kmx_destroy(ctx);
+    for (Rank& rk : ranks) kmx_destroy(rk.ctx);
     return EXIT_SUCCESS;
   } catch (const std::exception& e) {
     std::cerr << "[error] " << e.what() << "\n";      // reference: spdlog::error + exit(EXIT_FAILURE), src/kmtricks.cpp:109-123
-    if (ctx) kmx_destroy(ctx);
+    for (Rank& rk : ranks) if (rk.ctx) kmx_destroy(rk.ctx);
     return EXIT_FAILURE;
   }
 }

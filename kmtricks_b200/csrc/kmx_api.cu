@@ -104,6 +104,7 @@ struct kmx_ctx {
   int wlen = 0, max_nk = 0;
   std::string err;
   std::mutex mu;                   // arena, err, dev_bytes
+  std::mutex lanes_mu;             // lane creation
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
@@ -347,7 +348,7 @@ extern "C" void kmx_destroy(kmx_ctx* ctx)
   delete ctx;
 }
 
-#define LANE0 Lane* ln = ctx->lanes.empty() ? nullptr : ctx->lanes[0].get(); if (!ln) return KMX_ERR_STATE
+#define LANE0 Lane* ln = ctx->lanes.empty() ? nullptr : ctx->lanes[0].get(); if (!ln) return KMX_ERR_STATE; cudaSetDevice(ctx->device)
 
 extern "C" const char* kmx_last_error(const kmx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" uint64_t kmx_launch_count(const kmx_ctx* ctx)
@@ -926,6 +927,36 @@ extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* text
   ctx->active_lanes = 1;
   return first_err.load();
 }
+
+// ---- lane-addressed entry points (one host thread per lane)
+extern "C" int kmx_lanes(kmx_ctx* ctx, uint32_t n)
+{
+  if (!ctx || n < 1 || n > 8) return KMX_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  std::lock_guard<std::mutex> g(ctx->lanes_mu);
+  while (ctx->lanes.size() < n) { int rc = lane_create(ctx, (int)ctx->lanes.size()); if (rc) return rc; }
+  ctx->active_lanes = std::max(ctx->active_lanes, (int)n);
+  if (ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok < 0) {
+    size_t free_b = 0, tot_b = 0;
+    if (cudaMemGetInfo(&free_b, &tot_b) != cudaSuccess) return KMX_ERR_CUDA;
+    ctx->hist_ok = ctx->prm.window_bits * 4 * n < (free_b / 4) ? 1 : 0;
+  }
+  return KMX_OK;
+}
+#define LANE_N(idx) if (!ctx || (idx) >= ctx->lanes.size()) return KMX_ERR_ARG; cudaSetDevice(ctx->device); Lane* ln = ctx->lanes[idx].get()
+extern "C" int kmx_lane_superk_begin(kmx_ctx* ctx, uint32_t lane) { LANE_N(lane); return superk_begin(ln); }
+extern "C" int kmx_lane_superk_push_fastq(kmx_ctx* ctx, uint32_t lane, const char* text, size_t nbytes, int on_device)
+{
+  if (!text && nbytes) return KMX_ERR_ARG;
+  LANE_N(lane); return superk_push_fastq(ln, text, nbytes, on_device);
+}
+extern "C" int kmx_lane_superk_push_reads(kmx_ctx* ctx, uint32_t lane, const char* seqs, const uint64_t* off, size_t nseq)
+{
+  if (nseq && (!seqs || !off)) return KMX_ERR_ARG;
+  LANE_N(lane); return superk_push_reads(ln, seqs, off, nseq);
+}
+extern "C" int kmx_lane_superk_end(kmx_ctx* ctx, uint32_t lane, uint64_t* kmers_per_partition) { LANE_N(lane); return superk_end(ln, kmers_per_partition); }
+extern "C" int kmx_lane_count_sample(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min) { LANE_N(lane); return count_sample(ln, sample, hard_min); }
 
 extern "C" int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n)
 {

@@ -97,6 +97,7 @@ extern "C" int kmx_dist_owner(const kmx_ctx* ctx, uint32_t partition, int world)
 }
 
 // one batch on one lane: local sample -> buckets -> exchange -> count every rank's sample on my partitions
+// slot of rank g's sample i_local of this batch: g * n_local (samples per rank over the whole run) + i_local (slot_base included)
 static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const char* text, size_t nbytes, int on_device,
                       u32 hard_min, uint64_t* pinfo_out)
 {
@@ -177,7 +178,11 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
       ln->records.p = rbuf;
       rc = upload_bucket_meta(ln);
       ln->sample_ready = true;
-      for (int g = 0; g < G; g++) for (u32 p = 0; p < P; p++) ctx->lists[((size_t)g * n_local + i_local) * P + p] = ListRef();
+      for (int g = 0; g < G; g++) {
+        const size_t slot = (size_t)g * n_local + i_local;
+        if (slot < ctx->prm.nb_samples) for (u32 p = 0; p < P; p++) ctx->lists[slot * P + p] = ListRef();
+        else for (u32 p = myf; p < myl; p++) if (meta[(size_t)g * ML + P + 1 + p]) return fail(ln, KMX_ERR_ARG, "rank %d sent data for slot %zu >= nb_samples", g, slot);
+      }
       if (!rc) {
         rc = binned ? count_hash_binned(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data()) : KMX_BIN_FALLBACK;
         if (rc == KMX_BIN_FALLBACK && ctx->hist_ok == 1) rc = count_hash_hist(ln, 0, (u32)meta[3 * P + 1], wsmp.data(), wprt.data());
@@ -201,7 +206,7 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
     ln->records.p = rbuf + roff[g] * rec;
     rc = upload_bucket_meta(ln);
     ln->sample_ready = true;
-    if (!rc) rc = count_sample(ln, (u32)g * n_local + i_local, (u32)mg[3 * P + 1]);
+    if (!rc && (size_t)g * n_local + i_local < ctx->prm.nb_samples) rc = count_sample(ln, (u32)g * n_local + i_local, (u32)mg[3 * P + 1]);
   }
   ln->records = save_rec; ln->h_boff = save_boff; ln->h_kcnt = save_kcnt; ln->h_bcap = save_bcap; ln->h_cursor = save_cur;
   return rc;
@@ -210,13 +215,22 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
 extern "C" int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* const* texts, const size_t* nbytes, int on_device,
                                     const uint32_t* hard_min, uint64_t* kmers_per_partition)
 {
-  if (!ctx || !ctx->dist || (n_local && (!texts || !nbytes || !hard_min))) return KMX_ERR_ARG;
+  return kmx_dist_run_batch(ctx, n_local, texts, nbytes, on_device, hard_min, 0, n_local, kmers_per_partition);
+}
+
+extern "C" int kmx_dist_run_batch(kmx_ctx* ctx, uint32_t n_batch, const char* const* texts, const size_t* nbytes, int on_device,
+                                  const uint32_t* hard_min, uint32_t slot_base, uint32_t n_local, uint64_t* kmers_per_partition)
+{
+  if (!ctx || !ctx->dist || (n_batch && (!texts || !nbytes || !hard_min)) || (u64)slot_base + n_batch > n_local) return KMX_ERR_ARG;
   KmxDist* d = ctx->dist.get();
   const u32 P = ctx->prm.nb_partitions;
   const u32 nlanes = d->use_lanes ? std::min<u32>(d->use_lanes, (u32)d->comms.size()) : (u32)d->comms.size();
   {
     LANE0;
-    if ((u64)d->world * n_local > ctx->prm.nb_samples) return fail(ln, KMX_ERR_ARG, "nb_samples %u < world %d x n_local %u", ctx->prm.nb_samples, d->world, n_local);
+    // slots >= nb_samples may only hold empty padding samples (the last rank of a run whose sample count is not a multiple of the world)
+    for (u32 i = 0; i < n_batch; i++)
+      if ((u64)d->rank * n_local + slot_base + i >= ctx->prm.nb_samples && nbytes[i])
+        return fail(ln, KMX_ERR_ARG, "sample slot %llu >= nb_samples %u", (unsigned long long)((u64)d->rank * n_local + slot_base + i), ctx->prm.nb_samples);
     if (ctx->prm.key_kind == KMX_KEY_HASH && ctx->hist_ok < 0) {
       size_t free_b = 0, tot_b = 0;
       CK(cudaMemGetInfo(&free_b, &tot_b));
@@ -229,8 +243,8 @@ extern "C" int kmx_dist_run_samples(kmx_ctx* ctx, uint32_t n_local, const char* 
     cudaSetDevice(ctx->device);
     Lane* ln = ctx->lanes[t].get();
     // every rank walks the same (lane, sample) schedule, so the collectives of a lane's communicator match up
-    for (u32 i = t; i < n_local; i += nlanes) {
-      int rc = first_err.load() ? first_err.load() : dist_batch(ln, t, i, n_local, texts[i], nbytes[i], on_device, hard_min[i],
+    for (u32 i = t; i < n_batch; i += nlanes) {
+      int rc = first_err.load() ? first_err.load() : dist_batch(ln, t, slot_base + i, n_local, texts[i], nbytes[i], on_device, hard_min[i],
                                                                 kmers_per_partition ? kmers_per_partition + (size_t)i * P : nullptr);
       if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); return; }
     }

@@ -113,3 +113,88 @@ def test_cli_errors_are_loud(workdir):
     assert r.returncode != 0 and "error" in r.stderr.lower()
     r = subprocess.run([KMX, "pipeline", "--file", f"{workdir}/fof.txt", "--run-dir", f"{workdir}/x"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_streamed_blocks_and_gz_input(workdir):
+    """The host streams every FASTQ in blocks of whole records (--block-mib; here 1 MiB blocks over 6.3 MB files, several
+    lanes) and inflates .gz on the fly: same run directory as the reference, which reads the plain files."""
+    import gzip
+    d = workdir
+    a, _ = run_both(d, "base2", ["--kmer-size", "31", "--mode", "kmer:count:bin", "--hard-min", "2"])
+    with open(f"{d}/fof_gz.txt", "w") as f:
+        for line in open(f"{d}/fof.txt"):
+            sid, rest = line.split(":", 1)
+            if sid.strip() in ("S1", "S3"):
+                src = rest.split("!")[0].strip()
+                with open(src, "rb") as i, gzip.open(src + ".gz", "wb", compresslevel=1) as o:
+                    shutil.copyfileobj(i, o)
+                line = line.replace(src, src + ".gz")
+            f.write(line)
+    subprocess.run([KMX, "pipeline", "--file", f"{d}/fof_gz.txt", "--run-dir", f"{d}/kmx_blocks", "--nb-partitions", "8", "--minimizer-size", "10",
+                    "--static-repart", "--keep-tmp", "--kmer-size", "31", "--mode", "kmer:count:bin", "--hard-min", "2", "--block-mib", "1",
+                    "--threads", "3"], check=True)
+    for sub in ("matrices", "merge_infos", "partition_infos", "counts"):
+        same_files(a, f"{d}/kmx_blocks", sub)
+
+
+def test_plugin_applies_in_pa_mode_too(workdir):
+    """The reference calls the plugin for every merged row whatever the output mode (merge.hpp:249-257): here presence/absence
+    rows with the unchanged basic_ex plugin."""
+    so = os.path.join(PLUG, "libbasic_ex.so")
+    if not os.path.exists(so):
+        pytest.skip("reference plugins not built")
+    a, b = run_both(workdir, "plug_pa", ["--kmer-size", "31", "--mode", "kmer:pa:bin", "--hard-min", "1", "--plugin", so, "--plugin-config", "2"])
+    same_files(a, b, "matrices")
+    same_files(a, b, "merge_infos")
+
+
+def test_hash_bft_end_to_end_and_bf_files(workdir):
+    """--mode hash:bft:bin from the command line (the reference CLI cannot reach it at this commit): every
+    matrices/matrix_P.cmbf equals the file the reference's own HashMerger::write_as_bft writes from the reference's count
+    files, and every filters/<id>.bf holds, after its header and the u64 bit count, the sample's row of every partition."""
+    import numpy as np
+    d = workdir
+    harness = os.path.join(ROOT, "oracle", "_ref", "bin", "bft_harness")
+    if not os.path.exists(harness):
+        pytest.skip("bft_harness not built")
+    args = ["--kmer-size", "31", "--hard-min", "2", "--bloom-size", "2000000", "--soft-min", "2", "--share-min", "1"]
+    a, _ = run_both(d, "hash_bf2", args + ["--mode", "hash:bf:bin"])
+    b = f"{d}/kmx_bft"
+    subprocess.run([KMX, "pipeline", "--file", f"{d}/fof.txt", "--nb-partitions", "8", "--minimizer-size", "10", "--static-repart", "--run-dir", b,
+                    "--mode", "hash:bft:bin", "--threads", "3"] + args, check=True)
+    ids = [l.split(":")[0].strip() for l in open(f"{d}/fof.txt") if l.strip()]
+    W = int(np.frombuffer(open(f"{a}/hash.info", "rb").read()[16:24], dtype=np.uint64)[0])
+    rows = []
+    for p in range(8):
+        files = [f"{a}/counts/partition_{p}/{i}.hash" for i in ids]
+        subprocess.run([harness, "bft", f"{d}/bft_{p}", str(W * p), str(W * (p + 1) - 1), "2", "1", "1"] + files, check=True)
+        want = open(f"{d}/bft_{p}", "rb").read()
+        got = open(f"{b}/matrices/matrix_{p}.cmbf", "rb").read()
+        assert got == want, f"bft matrix {p}"
+        rows.append(got[49:])
+    for s, i in enumerate(ids):
+        bf = open(f"{b}/filters/{i}.bf", "rb").read()
+        assert len(bf) == 112 + 8 + 8 * (W // 8)
+        assert int(np.frombuffer(bf[112:120], dtype=np.uint64)[0]) == 8 * W
+        for p in range(8):
+            assert bf[120 + p * (W // 8):120 + (p + 1) * (W // 8)] == rows[p][s * (W // 8):(s + 1) * (W // 8)], f"{i}.bf partition {p}"
+
+
+def test_two_gpus_from_the_command_line(workdir):
+    """--devices 0-1: one in-process rank per GPU (samples sharded for stage 1, one NCCL exchange, partitions sharded for
+    count + merge); the run directory equals the reference's.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d = workdir
+    with open(f"{d}/fof4.txt", "w") as f:                 # the four FASTQ samples (one file each), hard-min override kept
+        for line in open(f"{d}/fof.txt"):
+            if line.startswith("S"):
+                f.write(line)
+    for tag, args in (("mg_hash", ["--kmer-size", "31", "--mode", "hash:bf:bin", "--hard-min", "2", "--bloom-size", "2000000"]),
+                      ("mg_kmer", ["--kmer-size", "63", "--mode", "kmer:count:bin", "--hard-min", "2", "--soft-min", "2"])):
+        common = ["pipeline", "--file", f"{d}/fof4.txt", "--nb-partitions", "8", "--minimizer-size", "10", "--static-repart", "--keep-tmp"] + args
+        subprocess.run([REF] + common + ["--run-dir", f"{d}/ref_{tag}", "-t", "4"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([KMX] + common + ["--run-dir", f"{d}/kmx_{tag}", "--devices", "0-1", "--threads", "2"], check=True)
+        for sub in ("matrices", "merge_infos", "partition_infos", "counts"):
+            same_files(f"{d}/ref_{tag}", f"{d}/kmx_{tag}", sub)

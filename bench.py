@@ -57,6 +57,13 @@ def parse_args():
                                                              "when steps+warmup would push the run past --ref-budget-s)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle-checked pass after timing")
+    ap.add_argument("--other-configs", default="auto", choices=["auto", "on", "off"],
+                    help="BASELINE configs 3-5 (1000 x 5M kmer:count, 1000 x 5M hash:bft, 500 x 5M k=63 kmer:pa + rescue) after the main "
+                         "measurement, reported under other_configs; auto = only on 8 GPUs, where they fit at full size")
+    ap.add_argument("--oc-child", default="", help=argparse.SUPPRESS)      # internal: run ONE other config in this (child) process
+    ap.add_argument("--oc-timeout-s", type=float, default=170.0, help="other_configs: hard limit per config (each runs in child processes)")
+    ap.add_argument("--oc-samples-scale", type=float, default=1.0, help="other_configs: fraction of the samples (testing on fewer GPUs)")
+    ap.add_argument("--oc-reads-scale", type=float, default=1.0, help="other_configs: fraction of the reads per sample")
     return ap.parse_args()
 
 
@@ -267,6 +274,132 @@ def main_reference(args):
         print(json.dumps(line))
     finally:
         shutil.rmtree(wd, ignore_errors=True)
+
+
+
+# --------------------------------------------------------------------------- BASELINE configs 3-5
+OTHER_CONFIGS = {
+    # SURVEY 8(d) "Synthetic inputs": generator parameters that bound the number of matrix rows
+    "cfg3": dict(what="1000 samples x 5M reads x 150 nt, k=31, kmer:count:bin, P=512, hard-min 3", samples=1000, reads=5_000_000, k=31,
+                 mode="kmer:count:bin", P=512, hard_min=3, genome=10_000_000, d=1e-5, e=1e-3,
+                 twin="tests/test_gpu_atscale.py::test_cfg345_twins_equal_reference_binary[cfg3_kmer_count_P512]"),
+    "cfg4": dict(what="1000 samples x 5M reads x 150 nt, k=31, hash:bft:bin (Bloom rows + bit transpose), P=512, bloom 4e8, hard-min 3", samples=1000,
+                 reads=5_000_000, k=31, mode="hash:bft:bin", P=512, hard_min=3, genome=10_000_000, d=1e-5, e=1e-3, bloom=400_000_000,
+                 twin="tests/test_gpu_atscale.py::test_cfg345_twins_equal_reference_binary[cfg4_hash_bft_P512]"),
+    "cfg5": dict(what="500 samples x 5M reads x 150 nt, k=63, kmer:pa:bin, P=256, hard-min 1, soft-min 3, share-min 2 (rescue)", samples=500,
+                 reads=5_000_000, k=63, mode="kmer:pa:bin", P=256, hard_min=1, soft_min=3, share_min=2, recurrence_min=1, genome=10_000_000,
+                 d=1e-4, e=2e-4, twin="tests/test_gpu_atscale.py::test_cfg345_twins_equal_reference_binary[cfg5_k63_kmer_pa_rescue_P256]"),
+}
+
+
+def run_other_config(name, c, args, world, rank, local, peak):
+    """One pass of the whole hot path over a BASELINE config that does not fit as text: the FASTQ of a batch of samples is
+    generated on the device (untimed), the batch goes through stage 1 / exchange / stage 2 (timed, CUDA events), the lists
+    stay resident; then every rank merges its partitions (timed).  Returns the line's entry for this config."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kmtricks_b200 import _lib, engine, synth
+    S = max(world, int(round(c["samples"] * args.oc_samples_scale)))
+    R = max(1000, int(round(c["reads"] * args.oc_reads_scale)))
+    Lr, k, P = 150, c["k"], c["P"]
+    cfg = engine.Config(kmer_size=k, nb_partitions=P, mode=c["mode"], hard_min=c["hard_min"], soft_min=c.get("soft_min", 1),
+                        recurrence_min=c.get("recurrence_min", 1), share_min=c.get("share_min", 0), bloom_size=c.get("bloom", 10_000_000))
+    n_local = (S + world - 1) // world
+    eng = engine.Engine(cfg, S, device=local)
+    L, h = eng.lib, eng.h
+
+    def ck(rc, what):
+        if rc:
+            raise RuntimeError(f"{name} {what}: {L.kmx_last_error(h).decode()} ({rc})")
+    try:
+        if world > 1:
+            from kmtricks_b200 import dist as kd
+            kd.init_engine(eng, nlanes=args.lanes)
+            my_parts = list(kd.owned_partitions(P, world, rank))
+        else:
+            my_parts = list(range(P))
+        sb = R * synth.record_bytes(Lr)
+        B = max(1, min(8, n_local))
+        d_text = C.c_void_p()
+        ck(L.kmx_dev_alloc(h, B * sb + 64, C.byref(d_text)), "dev_alloc")
+        stream = torch.cuda.ExternalStream(L.kmx_stream(h), device=torch.device("cuda", local))
+
+        def timed(fn):
+            ck(L.kmx_sync(h), "sync")
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            ck(L.kmx_sync(h), "sync"); torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        def batch(b0, timed_run):
+            nb = min(B, n_local - b0)
+            sizes = []
+            for i in range(nb):
+                slot = rank * n_local + b0 + i
+                if slot < S:
+                    ck(L.kmx_synth_fastq(h, 1234, slot, 0, R, Lr, c["genome"], c["d"], c["e"], 1, d_text.value + i * sb), "synth")
+                    sizes.append(sb)
+                else:
+                    sizes.append(0)                      # padding sample of the last rank
+            ck(L.kmx_sync(h), "sync")
+            ptrs = (C.c_void_p * nb)(*[d_text.value + i * sb for i in range(nb)])
+            sz = (C.c_size_t * nb)(*sizes)
+            hm = (C.c_uint32 * nb)(*([c["hard_min"]] * nb))
+            if world > 1:
+                fn = lambda: ck(L.kmx_dist_run_batch(h, nb, ptrs, sz, 1, hm, b0, n_local, None), "dist_run_batch")
+            else:
+                ids = (C.c_uint32 * nb)(*[min(b0 + i, S - 1) for i in range(nb)])
+                fn = lambda: ck(L.kmx_run_samples(h, nb, ptrs, sz, 1, ids, hm, args.lanes, None), "run_samples")
+            if timed_run:
+                return timed(fn)
+            fn()
+            return 0.0
+
+        batch(0, False)                                  # warm-up: allocations, bucket geometry, table sizes
+        ck(L.kmx_reset(h), "reset")
+        if world > 1:
+            dist.barrier()
+        ms_sc = 0.0
+        for b0 in range(0, n_local, B):
+            ms_sc += batch(b0, True)
+        soft = np.full(S, cfg.soft_min, dtype=np.uint32)
+        mp = _lib.KmxMergeParams(soft.ctypes.data_as(C.POINTER(C.c_uint32)), cfg.recurrence_min, cfg.share_min,
+                                 {"count": 0, "pa": 1, "bf": 2, "bft": 3}[cfg.fmt], 0)
+        res = _lib.KmxMergeResult()
+        body = [0, 0]
+
+        def merges():
+            for p in my_parts:
+                ck(L.kmx_merge_partition(h, p, C.byref(mp), C.byref(res)), "merge")
+                body[0] += res.n_rows * res.row_bytes; body[1] += res.n_rows
+        ms_merge = timed(merges)
+        D = 0
+        nsz = C.c_uint64()
+        for s_ in range(S):
+            for p_ in my_parts:
+                L.kmx_counts_size(h, s_, p_, C.byref(nsz)); D += nsz.value
+        tot = torch.tensor([ms_sc + ms_merge, ms_sc, ms_merge], device="cuda", dtype=torch.float64)
+        sums = torch.tensor([float(D), float(body[0]), float(body[1])], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX); dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        ms, ms_sc, ms_merge = [float(x) for x in tot.tolist()]
+        D, body_b, rows = [float(x) for x in sums.tolist()]
+        kmers = S * R * (Lr - k + 1)
+        w = (k + 31) // 32
+        key_b = 8 if cfg.key_kind == "hash" else 8 * w
+        bucket = BUCKET_BYTES_PER_KMER if k <= 32 else 1.17     # reference record density at k=63: (1 + ceil((63 + l - 1)/4)) / l, l ~ 18
+        alg = S * sb + 2 * bucket * kmers + 2 * (key_b + 4) * D + body_b * (2 if cfg.fmt == "bft" else 1)
+        return {"workload": c["what"], "value": kmers / (ms * 1e-3), "unit": "k-mers/s", "n_gpus": world, "ms_per_step": ms,
+                "ms_superk_exchange_count": ms_sc, "ms_merge": ms_merge, "kmers_per_step": kmers,
+                "scale": {"samples": S, "reads_per_sample": R, "full_size": S == c["samples"] and R == c["reads"]},
+                "surviving_key_sample_pairs": int(D), "matrix_rows": int(rows), "matrix_bytes": int(body_b),
+                "pipeline_roofline": {"algorithmic_bytes_per_step": alg, "achieved_GBps_per_gpu": alg / world / (ms * 1e-3) / 1e9,
+                                      "frac": alg / world / (ms * 1e-3) / 1e9 / peak, "peak": peak},
+                "steps": 1, "warmup": "one batch", "data": "synthetic, generated on the device per batch of <= 8 samples per GPU (untimed)",
+                "parity_twin": c["twin"], "device_bytes": int(L.kmx_device_bytes(h))}
+    finally:
+        eng.close()
 
 
 # --------------------------------------------------------------------------- kmx arm
@@ -538,6 +671,34 @@ def main_kmx(args):
         except Exception as e:      # the check must not take the measurement down with it
             parity = f"error: {e}"
 
+    # ---- BASELINE configs 3-5 (their own engines; the main one is closed first to free its HBM)
+    # Every rank starts a child process per config (same rank / world, its own rendezvous port) under a hard time limit, so a
+    # config that fails or hangs at full size is reported as such and cannot take the headline measurement down with it.
+    other = None
+    want_other = args.other_configs == "on" or (args.other_configs == "auto" and world == 8)
+    dev_bytes_main = int(L.kmx_device_bytes(h))
+    if want_other:
+        eng.close()
+        torch.cuda.empty_cache()
+        other = {}
+        t_oc = time.perf_counter()
+        for idx, (name, c) in enumerate(OTHER_CONFIGS.items()):
+            if time.perf_counter() - t_oc > 2.2 * args.oc_timeout_s:
+                other[name] = {"workload": c["what"], "skipped": "time budget of the other_configs block used up"}
+                continue
+            env = dict(os.environ)
+            env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 101 + idx)
+            env["TORCHELASTIC_USE_AGENT_STORE"] = "False"      # the children rendezvous among themselves (rank 0's child hosts the store)
+            cmd = [sys.executable, os.path.abspath(__file__), "--oc-child", name, "--gpus", str(world), "--lanes", str(args.lanes),
+                   "--oc-samples-scale", str(args.oc_samples_scale), "--oc-reads-scale", str(args.oc_reads_scale)]
+            try:
+                r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.oc_timeout_s)
+                out = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                other[name] = json.loads(out[-1]) if out else {"workload": c["what"], "error": (r.stderr or "no output")[-300:]}
+            except subprocess.TimeoutExpired:
+                other[name] = {"workload": c["what"], "error": f"no result within {args.oc_timeout_s:.0f} s"}
+            except Exception as e:
+                other[name] = {"workload": c["what"], "error": str(e)[:300]}
     if rank == 0:
         line = {"metric": "k-mers/s end-to-end (repart->merge)", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -548,16 +709,41 @@ def main_kmx(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "parity_check": parity, "exchange": exchange,
                 "kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in prof.items()}, "ms_per_step_1lane": ms_1lane,
-                "host_wall_ms_per_step": host_wall, "device_bytes": int(L.kmx_device_bytes(h))}
+                "host_wall_ms_per_step": host_wall, "device_bytes": dev_bytes_main, "other_configs": other}
         print(json.dumps(line))
-    eng.close()
+    if not want_other:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def main_oc_child(args):
+    """One other config in a process of its own (see main_kmx)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        peak = 6650.0
+    c = OTHER_CONFIGS[args.oc_child]
+    try:
+        res = run_other_config(args.oc_child, c, args, world, rank, local, peak)
+    except Exception as e:
+        res = {"workload": c["what"], "error": str(e)[:300]}
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    os._exit(0)                 # no teardown collectives: a rank that failed must not make the others wait
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.oc_child:
+        main_oc_child(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_kmx(a)

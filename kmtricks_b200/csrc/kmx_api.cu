@@ -116,6 +116,7 @@ struct kmx_ctx {
   u32 s1_len_hint = 0;             // longest FASTQ read seen so far: geometry of the self-indexing stage-1 launch (0 = none yet)
   double ht_factor = 0.5;          // table slots per k-mer occurrence (doubles after an overflow)
   bool ht_union_ok = true;
+  double union_factor = 2.5;       // slots of the merge's key-union set per entry of the largest list (grows with what the partitions show)
   bool prof_on = false;
   double prof_ms[KMX_PROF_KINDS] = {0};
   u64 prof_cnt[KMX_PROF_KINDS] = {0};

@@ -154,9 +154,17 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
   //    keys; otherwise (or if the set overflows): concatenate, sort, unique
   u64* ulo = nullptr; u64* uhi = nullptr; u64 nu = 0;
   bool have_union = false;
-  if (ctx->ht_union_ok) {
-    const u64 cap = next_pow2(std::max<u64>(4096, (u64)(2.5 * (double)max_n)));
-    if (cap < 0x7FFFFFFFULL) {
+  // The set is sized from the largest list times a factor learned from the partitions merged so far (samples that share
+  // most keys: ~1.3; samples with private keys, e.g. hard-min 1: hundreds), never beyond what tot_n entries can need; an
+  // overflow raises the factor and retries, so that one dissimilar partition does not send all the later ones to the
+  // concatenate + sort path.
+  for (int attempt = 0; ctx->ht_union_ok && !have_union && attempt < 3; attempt++) {
+    double factor;
+    { std::lock_guard<std::mutex> g(ctx->mu); factor = ctx->union_factor; }
+    const u64 want = (u64)(factor * (double)max_n);
+    const u64 cap = next_pow2(std::max<u64>(4096, std::min<u64>(want, 2 * tot_n)));
+    if (cap >= 0x7FFFFFFFULL) break;
+    {
       CK(ensure(ln, ctx->uni_lo2, cap * 8 * KW));                    // table
       CK(ensure(ln, ctx->uni_lo, cap * 8));                          // distinct keys, unordered
       CK(ensure(ln, ln->keys_lo, cap * 8)); CK(ensure(ln, ln->keys_lo2, cap * 8));
@@ -167,12 +175,18 @@ static int merge_sparse(Lane* ln, uint32_t partition, const kmx_merge_params* mp
       CK(cudaMemsetAsync(ctx->uni_lo2.p, 0xFF, cap * 8 * KW, ln->st));
       if (KW == 1) CK(launch_ht_union((const MergeList*)ctx->d_lists.p, N, max_n, (u64*)ctx->uni_lo2.p, nullptr, cap, d_ovf, (u64*)ln->keys_lo.p, d_cnt, ln->st, &ln->launches));
       else CK(launch_ht2_union((const MergeList*)ctx->d_lists.p, N, max_n, ctx->uni_lo2.p, cap, d_ovf, (u64*)ln->keys_lo.p, (u64*)ln->keys_hi.p, d_cnt, ln->st, &ln->launches));
-      u32* hres = (u32*)ln->h_pin;                                   // lists/soft staging was consumed by the H2D copies above
+      u32* hres = (u32*)ln->h_pin;                                   // lists/soft staging was consumed by the copy kernel above
+      { SmallCopyBatch b(ln); b.add(hres, d_cnt, 8); CK(b.go()); }
       CK(cudaStreamSynchronize(ln->st));
-      CK(cudaMemcpyAsync(hres, d_cnt, 8, cudaMemcpyDeviceToHost, ln->st));
-      CK(cudaStreamSynchronize(ln->st));
-      if (!hres[1]) {
+      if (hres[1]) {                                                 // overflow: a bigger set next time (and now, if it can still grow)
+        std::lock_guard<std::mutex> g(ctx->mu);
+        ctx->union_factor = std::max(ctx->union_factor, factor * 4.0);
+        if (cap >= next_pow2(2 * tot_n)) break;
+        continue;
+      }
+      {
         nu = hres[0];
+        { std::lock_guard<std::mutex> g(ctx->mu); ctx->union_factor = std::max(ctx->union_factor, 2.2 * (double)nu / (double)std::max<u64>(max_n, 1)); }
         u64 seg1[2] = {0, nu};
         CK(ensure(ln, ln->sort_work, radix_sort_work_bytes(1, seg1)));
         int alt = 0;

@@ -83,6 +83,20 @@ __device__ __forceinline__ void hb_sts16(u32 addr, u32 v) { asm volatile("st.sha
 __device__ __forceinline__ u32 hb_lds16(u32 addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ u32 hb_lds32(u32 addr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
+// TMA (1-D bulk copy) + mbarrier: a tile's records are one contiguous 8 KB run of the bucket region ("bucket page"); an elected
+// thread has the copy engine of the SM fetch the NEXT tile into the other half of a double buffer while the CTA hashes the
+// current one, and the CTA picks it up by waiting on the buffer's mbarrier (SASS: UBLKCP / SYNCS).
+__device__ __forceinline__ void hb_mbar_init(u32 mbar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void hb_mbar_expect_tx(u32 mbar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void hb_bulk_g2s(u32 dst, const void* src, u32 bytes, u32 mbar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void hb_mbar_wait(u32 mbar, u32 parity)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tHB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra HB_DONE;\n\tbra HB_WAIT;\n\tHB_DONE:\n\t}" :: "r"(mbar), "r"(parity) : "memory");
+}
+
 // NBMAX: capacity of the per-bin arrays (static shared memory).  FAST: 28 <= k <= 32 -- the bases after a record's first
 // k-mer fit one 64-bit word and the roll runs on 32-bit halves with the k-dependent shifts folded into constants.
 template <bool FAST, int NBMAX>
@@ -90,12 +104,14 @@ __global__ void __launch_bounds__(HB_THREADS, 4)
 hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
 {
   __shared__ __align__(16) uint16_t s_stage[HB_S];    // bin b: slots [b*C, b*C + C)
-  __shared__ uint4 s_rec[HB_TR];
+  __shared__ __align__(128) uint4 s_rec2[2][HB_TR];   // double buffer of record tiles, filled by bulk copies
+  __shared__ __align__(8) u64 s_mbar[2];
+  __shared__ u32 s_meta[2][4];                        // per buffer: ticket, window, first record of the tile, records in the tile
   __shared__ uint16_t s_perm[HB_TR];
   __shared__ u32 s_bcnt[NBMAX], s_gcnt[NBMAX], s_gdst[NBMAX];
   __shared__ u32 s_cnt[64], s_start[64];
   __shared__ u32 s_gmax[HB_GROUPS], s_ground[HB_GROUPS];
-  __shared__ u32 s_nrounds, s_next;
+  __shared__ u32 s_nrounds;
   const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
   const u32 NB = a.NB, C = HB_S / NB;
   const int k = a.k;
@@ -111,31 +127,47 @@ hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
   const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(a.records);
   // persistent, in-order tickets over (window, tile) items numbered window-major (tile_pref = prefix of tiles per window)
   const u32 total = __ldg(a.tile_pref + a.nwin);
-  u32 y = 0, nxt = 0;
-  if (tid == 0) { nxt = atomicAdd(a.tickets, 1u); s_next = nxt; }
-  for (u32 b = tid; b < NB; b += HB_THREADS) s_bcnt[b] = 0;
-  for (;;) {
-    __syncthreads();                               // previous tile fully consumed, s_next visible
-    const u32 item = s_next;
-    if (item >= total) break;
-    while (__ldg(a.tile_pref + y + 1) <= item) y++;            // tickets only grow: the window only moves forward
-    const u32 n = __ldg(a.bcnt + y);
-    const u64 b0 = __ldg(a.boff + y);
-    const u32 tile0 = (item - __ldg(a.tile_pref + y)) * HB_TR;
+  u32 ywin = 0;                                        // thread 0: window of the last ticket (tickets only grow)
+  // thread 0: describe ticket `item` in s_meta[buf] and start the bulk copy of its records into s_rec2[buf]
+  auto fetch = [&](u32 item, u32 buf) {
+    s_meta[buf][0] = item;
+    if (item >= total) return;
+    while (__ldg(a.tile_pref + ywin + 1) <= item) ywin++;
+    const u32 n = __ldg(a.bcnt + ywin);
+    const u32 tile0 = (item - __ldg(a.tile_pref + ywin)) * HB_TR;
     const u32 nt = min((u32)HB_TR, n - tile0);
+    s_meta[buf][1] = ywin; s_meta[buf][2] = tile0; s_meta[buf][3] = nt;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer's earlier (generic) reads are ordered before the copy's writes
+    const u32 mb = hb_saddr(&s_mbar[buf]);
+    hb_mbar_expect_tx(mb, nt * 16u);
+    hb_bulk_g2s(hb_saddr(&s_rec2[buf][0]), recs + __ldg(a.boff + ywin) + tile0, nt * 16u, mb);
+  };
+  if (tid == 0) {
+    hb_mbar_init(hb_saddr(&s_mbar[0]), 1); hb_mbar_init(hb_saddr(&s_mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fetch(atomicAdd(a.tickets, 1u), 0);
+  }
+  for (u32 b = tid; b < NB; b += HB_THREADS) s_bcnt[b] = 0;
+  u32 nxt = 0;
+  for (u32 it = 0;; it++) {
+    const u32 buf = it & 1u;
+    __syncthreads();                               // previous tile fully consumed, this tile's s_meta visible
+    if (s_meta[buf][0] >= total) break;
+    const u32 y = s_meta[buf][1];
+    const u32 nt = s_meta[buf][3];
+    const uint4* __restrict__ s_rec = s_rec2[buf];
     if (tid < 64) s_cnt[tid] = 0;
+    if (tid == 0) nxt = atomicAdd(a.tickets, 1u);   // next ticket: its latency hides behind the counting sort
     __syncthreads();
-    if (tid == 0) nxt = atomicAdd(a.tickets, 1u);   // next ticket: its latency hides behind this tile
-    // ---- load the tile, counting sort by k-mers per record
+    hb_mbar_wait(hb_saddr(&s_mbar[buf]), (it >> 1) & 1u);      // the tile's records have landed
+    // ---- counting sort by k-mers per record
     u32 nkr[HB_PER], rank[HB_PER];
 #pragma unroll
     for (int i = 0; i < HB_PER; i++) {
       const u32 r = tid + HB_THREADS * i;
       nkr[i] = 0; rank[i] = 0;
       if (r < nt) {
-        const uint4 v = __ldg(recs + b0 + tile0 + r);
-        s_rec[r] = v;
-        nkr[i] = ((v.w >> 24) - (u32)k + 1u) & 63u;
+        nkr[i] = ((s_rec[r].w >> 24) - (u32)k + 1u) & 63u;
         rank[i] = atomicAdd(&s_cnt[nkr[i]], 1u);
       }
     }
@@ -166,6 +198,7 @@ hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
         s_ground[g] = r; used += sz;
       }
       s_nrounds = r + 1;
+      fetch(nxt, buf ^ 1u);                         // the next tile's records travel while this tile is hashed
     }
     __syncthreads();
     const u32 nrounds = s_nrounds;
@@ -264,7 +297,6 @@ hash_bin_kernel(HashBinArgs a, FastMod32 fm32)
       // (no barrier: the next round's / tile's staging writes are ordered behind the barriers that follow)
       if (rd + 1 < nrounds) __syncthreads();
     }
-    if (tid == 0) s_next = nxt;
   }
 }
 
@@ -428,8 +460,8 @@ cudaError_t launch_hash_binned(const HashBinArgs& a, u32 total_tiles, int phase,
       if (fast) hash_bin_kernel<true, 128><<<grid, HB_THREADS, 0, st>>>(a, f32);
       else hash_bin_kernel<false, 128><<<grid, HB_THREADS, 0, st>>>(a, f32);
     } else {
-      if (fast) hash_bin_kernel<true, 1024><<<grid, HB_THREADS, 0, st>>>(a, f32);
-      else hash_bin_kernel<false, 1024><<<grid, HB_THREADS, 0, st>>>(a, f32);
+      if (fast) hash_bin_kernel<true, 512><<<grid, HB_THREADS, 0, st>>>(a, f32);
+      else hash_bin_kernel<false, 512><<<grid, HB_THREADS, 0, st>>>(a, f32);
     }
     *launches += 1;
   } else {
@@ -452,6 +484,6 @@ cudaError_t launch_hash_binned(const HashBinArgs& a, u32 total_tiles, int phase,
 }
 
 u32 hash_bin_tile_records() { return HB_TR; }
-u32 hash_bin_max_bins() { return 1024; }
+u32 hash_bin_max_bins() { return 512; }
 
 }  // namespace kmx

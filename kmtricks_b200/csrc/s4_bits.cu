@@ -11,16 +11,19 @@
 #include "common.cuh"
 #include "kmx_internal.h"
 
+#include <algorithm>
+
 namespace kmx {
 
 __global__ void __launch_bounds__(1024)
-transpose_bits_kernel(const uint8_t* __restrict__ in, u64 nrows, u64 ncols, uint8_t* __restrict__ out)
+transpose_bits_kernel(const uint8_t* __restrict__ in, u64 nrows, u64 ncols, uint8_t* __restrict__ out, int rows_in_x)
 {
   __shared__ u32 s_t[32][33];
   const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const u64 in_rb = ncols >> 3, out_rb = nrows >> 3;
-  const u64 c0 = (u64)blockIdx.x * 32;                   // first column (bit) of this CTA
-  const u64 rblk0 = (u64)blockIdx.y * 32;                // first 32-row block of this CTA
+  // the longer dimension goes to gridDim.x (gridDim.y stops at 65535): a Bloom window has millions of rows, its transpose millions of columns
+  const u64 c0 = (u64)(rows_in_x ? blockIdx.y : blockIdx.x) * 32;      // first column (bit) of this CTA
+  const u64 rblk0 = (u64)(rows_in_x ? blockIdx.x : blockIdx.y) * 32;   // first 32-row block of this CTA
   const u64 r = (rblk0 + w) * 32 + lane;                 // input row of this lane
   u32 word = 0;
   if (r < nrows) {
@@ -54,8 +57,11 @@ transpose_bits_kernel(const uint8_t* __restrict__ in, u64 nrows, u64 ncols, uint
 cudaError_t launch_transpose_bits(const uint8_t* in, u64 nrows, u64 ncols, uint8_t* out, cudaStream_t st, u64* launches)
 {
   if (!nrows || !ncols) return cudaSuccess;
-  dim3 grid((unsigned)((ncols + 31) / 32), (unsigned)((nrows + 1023) / 1024));
-  transpose_bits_kernel<<<grid, 1024, 0, st>>>(in, nrows, ncols, out);
+  const u64 gc = (ncols + 31) / 32, gr = (nrows + 1023) / 1024;
+  const int rows_in_x = gr >= gc;
+  if (std::min(gc, gr) > 65535 || std::max(gc, gr) > 0x7FFFFFFFULL) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)(rows_in_x ? gr : gc), (unsigned)(rows_in_x ? gc : gr));
+  transpose_bits_kernel<<<grid, 1024, 0, st>>>(in, nrows, ncols, out, rows_in_x);
   *launches += 1;
   return cudaGetLastError();
 }

@@ -120,3 +120,21 @@ def test_bad_parameters_fail_loudly():
     with pytest.raises(engine.KmxError):
         eng.count(0)                    # no sample finished
     eng.close()
+
+
+def test_transpose_of_a_window_beyond_65535_row_blocks():
+    """A Bloom window of more than 65535 x 1024 rows (large --bloom-size with few partitions): the row blocks go to gridDim.x,
+    and so do the column blocks of the way back (BitMatrix::transpose is an involution, bitmatrix.hpp:209-214)."""
+    from kmtricks_b200 import engine
+    rng = np.random.default_rng(3)
+    nrows, ncols = 68_000_000 // 8 * 8, 8
+    a = rng.integers(0, 256, nrows * ncols // 8, dtype=np.uint8)
+    eng = engine.Engine(engine.Config(kmer_size=31, nb_partitions=4, mode="kmer:count:bin"), 1)
+    try:
+        t = eng.transpose_bits(a, nrows, ncols)
+        want = np.packbits(np.unpackbits(a, bitorder="little").reshape(nrows, ncols).T.copy(), bitorder="little")
+        assert np.array_equal(t, want)
+        back = eng.transpose_bits(t, ncols, nrows)
+        assert np.array_equal(back, a)
+    finally:
+        eng.close()

@@ -61,7 +61,7 @@ def parse_args():
                     help="BASELINE configs 3-5 (1000 x 5M kmer:count, 1000 x 5M hash:bft, 500 x 5M k=63 kmer:pa + rescue) after the main "
                          "measurement, reported under other_configs; auto = only on 8 GPUs, where they fit at full size")
     ap.add_argument("--oc-child", default="", help=argparse.SUPPRESS)      # internal: run ONE other config in this (child) process
-    ap.add_argument("--oc-timeout-s", type=float, default=170.0, help="other_configs: hard limit per config (each runs in child processes)")
+    ap.add_argument("--oc-timeout-s", type=float, default=150.0, help="other_configs: hard limit per config (each runs in child processes)")
     ap.add_argument("--oc-samples-scale", type=float, default=1.0, help="other_configs: fraction of the samples (testing on fewer GPUs)")
     ap.add_argument("--oc-reads-scale", type=float, default=1.0, help="other_configs: fraction of the reads per sample")
     return ap.parse_args()
@@ -356,13 +356,21 @@ def run_other_config(name, c, args, world, rank, local, peak):
             fn()
             return 0.0
 
+        t_start = time.perf_counter()
+
+        def log(msg):
+            if rank == 0:
+                print(f"[{name} {time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+        log(f"S={S} R={R} world={world} n_local={n_local} B={B}")
         batch(0, False)                                  # warm-up: allocations, bucket geometry, table sizes
         ck(L.kmx_reset(h), "reset")
+        log("warm-up batch done")
         if world > 1:
             dist.barrier()
         ms_sc = 0.0
         for b0 in range(0, n_local, B):
             ms_sc += batch(b0, True)
+            log(f"batch {b0 // B + 1}/{(n_local + B - 1) // B}: {ms_sc:.0f} ms so far, device bytes {int(L.kmx_device_bytes(h)) >> 20} MiB")
         soft = np.full(S, cfg.soft_min, dtype=np.uint32)
         mp = _lib.KmxMergeParams(soft.ctypes.data_as(C.POINTER(C.c_uint32)), cfg.recurrence_min, cfg.share_min,
                                  {"count": 0, "pa": 1, "bf": 2, "bft": 3}[cfg.fmt], 0)
@@ -374,6 +382,7 @@ def run_other_config(name, c, args, world, rank, local, peak):
                 ck(L.kmx_merge_partition(h, p, C.byref(mp), C.byref(res)), "merge")
                 body[0] += res.n_rows * res.row_bytes; body[1] += res.n_rows
         ms_merge = timed(merges)
+        log(f"merges done: {ms_merge:.0f} ms")
         D = 0
         nsz = C.c_uint64()
         for s_ in range(S):
@@ -415,6 +424,11 @@ def main_kmx(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    t_begin = time.perf_counter()
+
+    def log(msg):                       # progress on stderr (rank 0): a run that is cut off still says how far it got
+        if rank == 0:
+            print(f"[bench {time.perf_counter() - t_begin:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
     # multi-GPU: samples shard over ranks (weak scaling: every rank parses `samples` samples)
     cfg = engine.Config(kmer_size=args.kmer_size, nb_partitions=args.partitions, mode=args.mode, hard_min=args.hard_min,
@@ -519,8 +533,10 @@ def main_kmx(args):
             ms = float(t.item())
         return ms
 
+    log(f"inputs generated ({N} samples per GPU, {world} GPU(s))")
     for _ in range(args.warmup):
         step_device()
+    log("warm-up done")
     launches0 = L.kmx_launch_count(h)
     wall.clear()
     sampler = ClockSampler(local)
@@ -531,6 +547,7 @@ def main_kmx(args):
     launches = (L.kmx_launch_count(h) - launches0) // max(args.steps, 1)
     ms_step = ms / args.steps
     value = world * kmers_step / (ms_step * 1e-3)
+    log(f"timed: {ms_step:.1f} ms/step")
 
     # per-kernel device time: same step, ONE lane (kernels back to back on one stream, so the
     # CUDA-event spans around each launch are exclusive), events recorded inside the library
@@ -550,6 +567,7 @@ def main_kmx(args):
         if cnt.value:
             prof[name] = {"ms_per_step": tms.value / psteps, "launches_per_step": cnt.value // psteps}
     ck(L.kmx_profile_enable(h, 0), "prof")
+    log(f"1-lane profile pass done: {ms_1lane:.1f} ms/step")
     if world > 1:
         ck(L.kmx_dist_set_lanes(h, args.lanes), "dist_set_lanes")
     exchange = None
@@ -658,18 +676,29 @@ def main_kmx(args):
                    "host_text_samples": K}
             L.kmx_host_free(h_text); L.kmx_host_free(h_out)
 
+    log(f"e2e done: {e2e}")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
 
-    # ---- N > 1: the path just timed, on small seeded samples, against the CPU oracle (the checker; tests/dist_check.py)
+    # ---- N > 1: the path just timed, on small seeded samples, against the CPU oracle (the checker; tests/dist_check.py).
+    # Runs in child processes (one per rank, own rendezvous port) under a time limit: a check that fails or hangs is
+    # reported as such and cannot take the measurement down with it.
     parity = None
     if world > 1 and not args.no_parity_check:
+        env = dict(os.environ)
+        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 100)
+        env["TORCHELASTIC_USE_AGENT_STORE"] = "False"
         try:
-            from tests import dist_check
-            parity = "ok" if dist_check.check(rank, world, local, quiet=True) else "FAIL"
-        except Exception as e:      # the check must not take the measurement down with it
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--oc-child", "parity", "--gpus", str(world)], env=env,
+                               capture_output=True, text=True, timeout=180)
+            out = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            parity = json.loads(out[-1])["parity_check"] if out else ("ok" if r.returncode == 0 and rank != 0 else f"error: {(r.stderr or 'no output')[-200:]}")
+        except subprocess.TimeoutExpired:
+            parity = "no result within 180 s"
+        except Exception as e:
             parity = f"error: {e}"
+        log(f"parity check: {parity}")
 
     # ---- BASELINE configs 3-5 (their own engines; the main one is closed first to free its HBM)
     # Every rank starts a child process per config (same rank / world, its own rendezvous port) under a hard time limit, so a
@@ -695,8 +724,14 @@ def main_kmx(args):
                 r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.oc_timeout_s)
                 out = [l for l in r.stdout.splitlines() if l.startswith("{")]
                 other[name] = json.loads(out[-1]) if out else {"workload": c["what"], "error": (r.stderr or "no output")[-300:]}
-            except subprocess.TimeoutExpired:
-                other[name] = {"workload": c["what"], "error": f"no result within {args.oc_timeout_s:.0f} s"}
+                log(f"{name}: {str(other[name])[:200]}")
+            except subprocess.TimeoutExpired as e:
+                tail = e.stderr.decode(errors="replace") if isinstance(e.stderr, bytes) else (e.stderr or "")
+                tail = " | ".join(l for l in tail.splitlines() if l.startswith("["))[-400:]
+                other[name] = {"workload": c["what"], "error": f"no result within {args.oc_timeout_s:.0f} s", "progress": tail}
+                for rest in list(OTHER_CONFIGS)[idx + 1:]:
+                    other[rest] = {"workload": OTHER_CONFIGS[rest]["what"], "skipped": "an earlier config ran into the time limit"}
+                break
             except Exception as e:
                 other[name] = {"workload": c["what"], "error": str(e)[:300]}
     if rank == 0:
@@ -729,6 +764,15 @@ def main_oc_child(args):
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
     except Exception:
         peak = 6650.0
+    if args.oc_child == "parity":
+        try:
+            from tests import dist_check
+            res = {"parity_check": "ok" if dist_check.check(rank, world, local, quiet=True) else "FAIL"}
+        except Exception as e:
+            res = {"parity_check": f"error: {str(e)[:200]}"}
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        os._exit(0)
     c = OTHER_CONFIGS[args.oc_child]
     try:
         res = run_other_config(args.oc_child, c, args, world, rank, local, peak)

@@ -599,14 +599,14 @@ def main_kmx(args):
             what = "S1: FASTQ text read + super-k-mer buckets written (1.03 B/k-mer)"
         elif top in ("hash_hist", "expand", "radix_sort", "rle", "hash_emit"):
             alg = BUCKET_BYTES_PER_KMER * kmers_launch
-            what = "S2: buckets read (1.03 B/k-mer) [+12 B per surviving (key,sample)]"
+            what = "S2: buckets read (1.03 B/k-mer) [+12 B per surviving (key,sample)]; hash_hist = pass A (hash + bin), hash_emit = pass B (count + emit)"
         else:
             alg = body_sum[0] / max(len(my_parts), 1)
             what = "S3/S4: matrix body written"
         ach = alg / (dur_ms * 1e-3) / 1e9
         traffic = None
         try:      # dram__bytes_read+write per sample launch of this span's kernels, from the committed ncu --set full capture (same launch shape only)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["spans"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["spans"]
             if top in tr and args.reads == 1_000_000 and args.read_len == 150 and args.mode == "hash:bf:bin" and args.partitions == 64 and args.bloom_size == 200_000_000:
                 traffic = tr[top]["dram_read_bytes"] + tr[top]["dram_write_bytes"]
         except Exception:

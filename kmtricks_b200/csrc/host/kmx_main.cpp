@@ -498,6 +498,19 @@ int main(int argc, char** argv)
       }
       return EXIT_SUCCESS;
     }
+    if (argc == 4 && std::string(argv[1]) == "blocks") {  // host-side check, no device: how a FASTQ file is cut into blocks of whole records
+      FastqBlocks fb(argv[2]);
+      std::vector<char> buf(std::stoull(argv[3]));
+      uint64_t h = 1469598103934665603ULL, total = 0;      // FNV-1a of the concatenated blocks
+      for (size_t n; (n = fb.next(buf.data(), buf.size())) != 0;) {
+        size_t lines = 0; for (size_t i = 0; i < n; i++) lines += buf[i] == '\n';
+        for (size_t i = 0; i < n; i++) { h ^= (unsigned char)buf[i]; h *= 1099511628211ULL; }
+        total += n;
+        std::cout << n << "\t" << lines << "\t" << (int)(buf[0] == '@') << "\n";
+      }
+      std::cout << "total\t" << total << "\t" << h << "\n";
+      return EXIT_SUCCESS;
+    }
     Run R;
     R.o = parse(argc, argv);
     const Options& o = R.o;

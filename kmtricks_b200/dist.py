@@ -58,3 +58,16 @@ def init_engine(eng, nlanes: int = 2):
     raw = (C.c_uint8 * (128 * nlanes)).from_buffer_copy(ids[0])
     eng._ck(L.kmx_dist_init(eng.h, rank, world, nlanes, raw), "dist_init")
     return rank, world
+
+
+def run_layout(n_samples: int, world: int, batch: int):
+    """Batches of a streamed multi-GPU run (what `kmx pipeline --devices` and bench.py's other_configs do): rank r parses the
+    samples [r*nl, (r+1)*nl), nl = ceil(n_samples / world), in batches of `batch`; every rank makes the same number of
+    kmx_dist_run_batch calls with the same (n, slot_base, nl) -- slots >= n_samples are empty padding samples.
+    Returns nl and, per batch, (slot_base, n, [per-rank list of global sample indices or None for padding])."""
+    nl = (n_samples + world - 1) // world
+    out = []
+    for b0 in range(0, nl, batch):
+        n = min(batch, nl - b0)
+        out.append((b0, n, [[(r * nl + b0 + i if r * nl + b0 + i < n_samples else None) for i in range(n)] for r in range(world)]))
+    return nl, out

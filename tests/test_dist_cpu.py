@@ -77,3 +77,21 @@ def test_exchange_plan_is_consistent_across_two_gloo_ranks(P):
     res = [q.get(timeout=120) for _ in procs]
     for p in procs: p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_streamed_run_layout_covers_every_sample_once_with_padding_at_the_end():
+    for n_samples, world, batch in ((500, 8, 8), (1000, 8, 8), (5, 2, 4), (7, 4, 3), (1, 2, 8), (16, 8, 4)):
+        nl, batches = kd.run_layout(n_samples, world, batch)
+        assert nl * world >= n_samples and (nl - 1) * world < n_samples
+        seen = []
+        for b0, n, per_rank in batches:
+            assert len(per_rank) == world and all(len(x) == n for x in per_rank)         # every rank: same call sequence
+            for r, slots in enumerate(per_rank):
+                for i, s in enumerate(slots):
+                    if s is not None:
+                        assert s == kd.global_slot(r, nl, b0 + i)
+                        seen.append(s)
+                    else:
+                        assert kd.global_slot(r, nl, b0 + i) >= n_samples               # padding only beyond the last sample
+        assert sorted(seen) == list(range(n_samples))
+        assert sum(n for _, n, _ in batches) == nl

@@ -71,3 +71,98 @@ def test_cli_fof_parser_kat_from_fof_test(tmp_path):
         f.write_text(bad)
         r = subprocess.run([kmx, "fof", str(f)], capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()
+
+
+def test_cli_streams_fastq_in_blocks_of_whole_records(tmp_path):
+    """The host's streaming reader (`kmx blocks <file> <block bytes>`, no device needed): every block but the last ends on
+    a record boundary (lines a multiple of 4, first byte '@'), the blocks concatenate to the file -- plain and gzipped, LF and
+    CRLF, with '@' as the first quality character, a last line without a newline; a record larger than a block is an error."""
+    import gzip
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    kmx = os.path.join(root, "kmtricks_b200", "bin", "kmx")
+    if not os.path.exists(kmx):
+        subprocess.run(["bash", os.path.join(root, "build.sh")], check=True)
+
+    def fnv(b):
+        h = 1469598103934665603
+        for x in b:
+            h = ((h ^ x) * 1099511628211) & (2**64 - 1)
+        return h
+    rng = np.random.default_rng(4)
+    recs = []
+    for i in range(400):
+        L = int(rng.integers(20, 200))
+        seq = bytes(rng.choice(list(b"ACGTN"), L).tolist())
+        recs.append(b"@r%d some comment\n" % i + seq + b"\n+\n" + b"@" * L + b"\n")       # '@' opens the quality line
+    text = b"".join(recs)
+    cases = {"plain.fastq": text, "crlf.fastq": text.replace(b"\n", b"\r\n"), "nonl.fastq": text[:-1]}
+    for name, data in cases.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        gz = tmp_path / (name + ".gz")
+        with gzip.open(gz, "wb") as g:
+            g.write(data)
+        for path in (p, gz):
+            for block in (700, 4096, 10**7):
+                out = subprocess.run([kmx, "blocks", str(path), str(block)], capture_output=True, text=True, check=True).stdout.split("\n")
+                rows = [l.split("\t") for l in out if l and not l.startswith("total")]
+                tot = [l.split("\t") for l in out if l.startswith("total")][0]
+                assert int(tot[1]) == len(data) and int(tot[2]) == fnv(data)
+                assert sum(int(r[0]) for r in rows) == len(data)
+                for r in rows[:-1]:
+                    assert int(r[0]) <= block and int(r[1]) % 4 == 0 and int(r[1]) > 0 and r[2] == "1"
+                assert rows[-1][2] == "1"
+                if block >= len(data):
+                    assert len(rows) == 1
+    r = subprocess.run([kmx, "blocks", str(tmp_path / "plain.fastq"), "100"], capture_output=True, text=True)
+    assert r.returncode != 0 and "block" in r.stderr
+
+
+def test_hash_mod_halves():
+    """The hand-scheduled 32-bit formulation of XXH64(8 bytes, seed 0) and of the Barrett modulo that stage 2's pass A runs
+    (hb_hash_mod, csrc/s2_bin.cu) -- restated here step for step on Python integers -- equals xxHash's XXH64 (the `xxhash`
+    package when present, else the oracle's C restatement) followed by `% d`, for the window sizes in use and for edge values."""
+    import random
+    M32, M64 = (1 << 32) - 1, (1 << 64) - 1
+    P1, P2, P3, P4, P5 = 0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x85EBCA77C2B2AE63, 0x27D4EB2F165667C5
+    try:
+        import xxhash
+        ref = lambda w: xxhash.xxh64(int(w).to_bytes(8, "little"), seed=0).intdigest()
+    except ImportError:
+        ref = lambda w: int(O.xxh64_u64(np.array([w], dtype=np.uint64))[0])
+
+    def fsl(lo, hi, s): return ((((hi << 32) | lo) << s) >> 32) & M32
+    def fsr(lo, hi, s): return (((hi << 32) | lo) >> s) & M32
+
+    def mul64(l, h, C):
+        t = l * (C & M32)
+        return t & M32, ((t >> 32) + l * (C >> 32) + h * (C & M32)) & M32
+
+    def fast(w, d):
+        l, h = mul64(w & M32, w >> 32, P2)
+        l, h = fsl(h, l, 31), fsl(l, h, 31)
+        l, h = mul64(l, h, P1)
+        h0 = (P5 + 8) & M64
+        l ^= h0 & M32; h ^= h0 >> 32
+        l, h = fsl(h, l, 27), fsl(l, h, 27)
+        t = (l * (P1 & M32) + P4) & M64
+        l, h = t & M32, ((t >> 32) + l * (P1 >> 32) + h * (P1 & M32)) & M32
+        l ^= h >> 1
+        l, h = mul64(l, h, P2)
+        l, h = l ^ fsr(l, h, 29), h ^ (h >> 29)
+        l, h = mul64(l, h, P3)
+        l ^= h
+        assert ((h << 32) | l) == ref(w)
+        m64 = M64 // d; ml, mh = m64 & M32, m64 >> 32
+        s = l * mh
+        t2 = h * ml + (s & M32)
+        q = (h * mh + (s >> 32) + (t2 >> 32)) & M32
+        r = (l - q * d) & M32
+        r = min(r, (r - d) & M32)
+        return min(r, (r - d) & M32)
+    rnd = random.Random(7)
+    for d in (3125056, 781312, 50048, 64, 2**30 - 64, 999983):
+        for w in [0, 1, M64, (1 << 62) - 1, d, d - 1] + [rnd.getrandbits(rnd.choice([10, 40, 62, 64])) for _ in range(3000)]:
+            assert fast(w, d) == ref(w) % d

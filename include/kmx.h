@@ -79,6 +79,15 @@ int kmx_superk_push_reads(kmx_ctx* ctx, const char* seqs, const uint64_t* off, s
  * partition_infos/<id>.pinfo (gatb_utils.hpp:46-51).  May be NULL.                          */
 int kmx_superk_end(kmx_ctx* ctx, uint64_t* kmers_per_partition);
 
+/* Repartition estimate on the device -- RepartTask (task.hpp:170-222) samples the banks on the CPU
+ * (gatb RepartitionAlgorithm.cpp:395-492) to balance the partitions; here: while enabled, every stage-1 launch of this
+ * context also adds each super-k-mer's k-mers to the load of its minimizer.  Run a sample of the input through
+ * kmx_superk_* on a context created with any table, read the 4^m loads, assign minimizers to partitions (the host does
+ * the longest-processing-time assignment, kmx_main.cpp: balanced_table) and create the real context with that table.
+ * (A stage-1 launch that is redone after a bucket overflow counts twice: an estimate, not an exact census.)             */
+int kmx_minimizer_load_enable(kmx_ctx* ctx, int on);
+int kmx_minimizer_load_get(kmx_ctx* ctx, uint64_t* load /* [4^m] */);
+
 /* ---- stage 2: CountTask / HashCountTask::exec (task.hpp:367-495) ------------------------
  * replaces KmerPartCounter / HashPartCounter::execute (gatb/sorting_count.hpp:637-650,934-943)
  * + Kmer/HashCountProcessor (gatb/count_processor.hpp:61-70,135-146): for every partition of

@@ -49,6 +49,8 @@ SYMBOLS = {
     "kmx_dist_owner": (_i, [_vp, _u32, _i]),
     "kmx_dist_set_lanes": (_i, [_vp, _u32]),
     "kmx_dist_run_batch": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), _u32, _u32, C.POINTER(_u64)]),
+    "kmx_minimizer_load_enable": (_i, [_vp, _i]),
+    "kmx_minimizer_load_get": (_i, [_vp, _vp]),
     "kmx_lanes": (_i, [_vp, _u32]),
     "kmx_lane_superk_begin": (_i, [_vp, _u32]),
     "kmx_lane_superk_push_fastq": (_i, [_vp, _u32, _vp, _sz, _i]),

@@ -43,7 +43,8 @@ struct Options {
   std::string fof, dir, mode = "kmer:count:bin", repart_from, until = "all", plugin, plugin_config;
   uint32_t k = 31, m = 10, P = 0, hard_min = 2, soft_min = 1, rec_min = 1, share_min = 0, threads = 4;
   uint64_t bloom = 10000000;
-  bool keep_tmp = false, static_repart = true;
+  bool keep_tmp = false, static_repart = true, balanced_repart = false;
+  size_t repart_sample_mib = 64;     // --balanced-repart: text sampled from the head of each of up to 16 samples
   int device = 0;
   std::vector<int> devices;          // --devices a-b | a,b,c : partitions sharded over these GPUs (one in-process rank per GPU)
   size_t block_mib = 256;            // FASTQ is streamed to the device in blocks of this many MiB (whole records)
@@ -55,7 +56,7 @@ struct Options {
   if (why) std::cerr << "kmx: " << why << "\n";
   std::cerr << "usage: kmx pipeline --file <fof> --run-dir <dir> --nb-partitions <P> [--kmer-size 31]\n"
                "           [--mode <kmer|hash>:<count|pa|bf|bft>:bin] [--hard-min 2] [--soft-min 1] [--recurrence-min 1]\n"
-               "           [--share-min 0] [--minimizer-size 10] [--bloom-size 10000000] [--static-repart | --repart-from <run-dir>]\n"
+               "           [--share-min 0] [--minimizer-size 10] [--bloom-size 10000000] [--static-repart | --repart-from <run-dir> | --balanced-repart]\n"
                "           [--until all|superk|count|merge] [--keep-tmp] [--threads 4] [--plugin lib.so [--plugin-config s]] [--device 0 | --devices 0-7] [--block-mib 256]\n";
   std::exit(why ? EXIT_FAILURE : EXIT_SUCCESS);
 }
@@ -79,6 +80,8 @@ Options parse(int argc, char** argv)
     else if (a == "--minimizer-size") o.m = std::stoul(need(i));
     else if (a == "--bloom-size") o.bloom = std::stoull(need(i));
     else if (a == "--static-repart") o.static_repart = true;
+    else if (a == "--balanced-repart") { o.balanced_repart = true; o.static_repart = false; }
+    else if (a == "--repart-sample-mib") o.repart_sample_mib = std::stoull(need(i));
     else if (a == "--repart-from") { o.repart_from = need(i); o.static_repart = false; }
     else if (a == "--until") o.until = need(i);
     else if (a == "--keep-tmp") o.keep_tmp = true;
@@ -318,6 +321,56 @@ std::string howde_header(uint32_t k, uint64_t bloom_bits)
   return h;
 }
 
+// ---------------------------------------------------------------------------- balanced repartition (RepartTask, task.hpp:170-222)
+// The reference samples the banks on the CPU and spreads the minimizers over the partitions by estimated load
+// (gatb RepartitionAlgorithm.cpp:395-492, PartiInfo.cpp:48-106).  Here the head of each of up to 16 samples goes through stage 1 on
+// the device with the minimizer-load counters on (kmx_minimizer_load_*), and the host assigns the minimizers heaviest first to
+// the lightest partition (longest-processing-time rule); minimizers the sample never showed keep their static place.  The result
+// is written as repartition_gatb/repartition.minimRepart, which the reference accepts through --repart-from.
+std::vector<uint16_t> balanced_table(const Options& o, const std::vector<Sample>& samples, const std::vector<uint16_t>& static_table)
+{
+  const size_t tn = static_table.size();
+  kmx_params prm{};
+  prm.kmer_size = o.k; prm.minim_size = o.m; prm.nb_partitions = o.P; prm.key_kind = KMX_KEY_KMER; prm.window_bits = 0;
+  prm.repart_table = static_table.data(); prm.nb_samples = 1;
+  kmx_ctx* ctx = nullptr;
+  if (int rc = kmx_create(o.devices[0], &prm, &ctx)) { std::string e = ctx ? kmx_last_error(ctx) : "failed"; if (ctx) kmx_destroy(ctx); throw Error("kmx_create (repartition estimate): " + e + " (code " + std::to_string(rc) + ")"); }
+  std::vector<uint64_t> load(tn, 0);
+  try {
+    KX(kmx_minimizer_load_enable(ctx, 1));
+    std::vector<char> buf(o.repart_sample_mib << 20);
+    const size_t step = std::max<size_t>(1, samples.size() / 16);
+    for (size_t s = 0; s < samples.size(); s += step) {
+      KX(kmx_superk_begin(ctx));
+      FastqBlocks fb(samples[s].files[0]);
+      const size_t n = fb.next(buf.data(), buf.size());
+      int rc = (n && buf[0] == '@') ? kmx_superk_push_fastq(ctx, buf.data(), n, 0) : KMX_ERR_FORMAT;
+      if (rc == KMX_ERR_FORMAT) {                          // FASTA / multi-line: the head of the file through the kseq-style parser
+        std::string text(buf.data(), n), seqs; std::vector<uint64_t> off;
+        parse_fastx(text, seqs, off);
+        if (off.size() > 2) { off.pop_back(); KX(kmx_superk_push_reads(ctx, seqs.data(), off.data(), off.size() - 1)); }   // the last record may be cut
+      } else if (rc) throw Error(std::string("kmx_superk_push_fastq: ") + kmx_last_error(ctx));
+      KX(kmx_superk_end(ctx, nullptr));
+    }
+    KX(kmx_minimizer_load_get(ctx, load.data()));
+  } catch (...) { kmx_destroy(ctx); throw; }
+  kmx_destroy(ctx);
+  std::vector<uint32_t> order;
+  for (size_t x = 0; x < tn; x++) if (load[x]) order.push_back((uint32_t)x);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return load[a] > load[b]; });
+  std::vector<uint16_t> table = static_table;
+  std::vector<std::pair<uint64_t, uint32_t>> heap;        // (load, partition), min-heap
+  for (uint32_t p = 0; p < o.P; p++) heap.push_back({0, p});
+  auto cmp = [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) { return a > b; };
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  for (uint32_t x : order) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    table[x] = (uint16_t)heap.back().second; heap.back().first += load[x];
+    std::push_heap(heap.begin(), heap.end(), cmp);
+  }
+  return table;
+}
+
 // ---------------------------------------------------------------------------- one GPU (one rank)
 struct Rank {
   int device = 0; kmx_ctx* ctx = nullptr;
@@ -539,8 +592,9 @@ int main(int argc, char** argv)
     // ---- repartition table (RepartTask, task.hpp:170-222)
     const size_t tn = (size_t)1 << (2 * o.m);
     std::vector<uint16_t> table(tn);
-    if (o.static_repart) for (size_t x = 0; x < tn; x++) table[x] = (uint16_t)(xxh64_u32((uint32_t)x) % P);
-    else {
+    if (o.static_repart || o.balanced_repart) for (size_t x = 0; x < tn; x++) table[x] = (uint16_t)(xxh64_u32((uint32_t)x) % P);
+    if (o.balanced_repart) table = balanced_table(o, R.samples, table);
+    else if (!o.static_repart) {
       std::ifstream in(o.repart_from + "/repartition_gatb/repartition.minimRepart", std::ios::binary);
       if (!in) throw Error("Unable to read at " + o.repart_from + "/repartition_gatb/repartition.minimRepart");
       uint16_t fp, npass; uint64_t fn;

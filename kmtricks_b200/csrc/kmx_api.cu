@@ -122,6 +122,7 @@ struct kmx_ctx {
   u64 prof_cnt[KMX_PROF_KINDS] = {0};
   void* merge_out = nullptr; size_t merge_out_cap = 0;
   uint16_t* d_repart = nullptr;
+  u64* d_mload = nullptr;          // minimizer loads (kmx_minimizer_load_enable)
   std::vector<std::unique_ptr<Lane>> lanes;
   std::vector<ArenaBlock> arena;
   std::vector<ListRef> lists;      // [N*P]
@@ -346,6 +347,7 @@ extern "C" void kmx_destroy(kmx_ctx* ctx)
   arena_clear(ctx);
   for (void* p : ctx->user_allocs) cudaFree(p);
   if (ctx->d_repart) cudaFree(ctx->d_repart);
+  if (ctx->d_mload) cudaFree(ctx->d_mload);
   delete ctx;
 }
 
@@ -498,6 +500,7 @@ static int run_s1(Lane* ln, const uint8_t* d_text, u64 text_bytes, const u32* d_
     a.cursor = ln->d_cursor; a.kcnt = ln->d_kcnt; a.overflow = ln->d_flags + 2;
     a.pack_words = (max_len + 15) / 16; if (a.pack_words < 1) a.pack_words = 1;
     a.stage_cap = 2048; a.flush_thr = 2048 - 1152;
+    a.mload = ctx->d_mload;
     { PROF(KMX_PROF_S1);
       s1v5::Geo geo; size_t smem5 = 0;
       if (fi) {
@@ -1194,6 +1197,32 @@ extern "C" int kmx_set_merge_output(kmx_ctx* ctx, void* dev_ptr, size_t cap_byte
 {
   if (!ctx) return KMX_ERR_ARG;
   ctx->merge_out = dev_ptr; ctx->merge_out_cap = dev_ptr ? cap_bytes : 0;
+  return KMX_OK;
+}
+
+// ---- repartition estimate (RepartTask, task.hpp:170-222 -> RepartitionAlgorithm.cpp:395-492 samples the banks on the CPU)
+extern "C" int kmx_minimizer_load_enable(kmx_ctx* ctx, int on)
+{
+  if (!ctx) return KMX_ERR_ARG;
+  LANE0;
+  int rc = kmx_sync(ctx);
+  if (rc) return rc;
+  const size_t tn = (size_t)1 << (2 * ctx->prm.minim_size);
+  if (on) {
+    if (!ctx->d_mload) { CK(cudaMalloc(&ctx->d_mload, tn * 8)); add_bytes(ctx, (long long)(tn * 8)); }
+    CK(cudaMemsetAsync(ctx->d_mload, 0, tn * 8, ln->st));
+    CK(cudaStreamSynchronize(ln->st));
+  } else if (ctx->d_mload) { CK(cudaFree(ctx->d_mload)); ctx->d_mload = nullptr; add_bytes(ctx, -(long long)(tn * 8)); }
+  return KMX_OK;
+}
+extern "C" int kmx_minimizer_load_get(kmx_ctx* ctx, uint64_t* load)
+{
+  if (!ctx || !load) return KMX_ERR_ARG;
+  LANE0;
+  if (!ctx->d_mload) return fail(ln, KMX_ERR_STATE, "kmx_minimizer_load_get without kmx_minimizer_load_enable");
+  int rc = kmx_sync(ctx);
+  if (rc) return rc;
+  CK(cudaMemcpy(load, ctx->d_mload, ((size_t)1 << (2 * ctx->prm.minim_size)) * 8, cudaMemcpyDeviceToHost));
   return KMX_OK;
 }
 

@@ -32,6 +32,7 @@ struct S1Args {
   u32 pack_words;               // 32-bit words of packed bases kept per segment = ceil(max segment length / 16)
   u32 stage_cap;                // staging capacity (cut events)
   u32 flush_thr;                // flush when staged > flush_thr
+  u64* mload;                   // NULL, or [4^m]: every record adds its k-mers to the load of its minimizer (repartition estimate)
 };
 size_t s1_smem_bytes(u32 pack_words, u32 stage_cap, int wlen, u32 P);
 u64 fq_num_tiles(const uint8_t* text, u64 nbytes);

@@ -407,6 +407,7 @@ s1_superk(const S1Args a)
             const u32 q = w * S1_EVW + r;
             const uint2 e = s_ev[q];
             const u32 p = __ldg(repart + e.y);              // e.y = minimizer of the record (Repartitor, PartiInfo.hpp:381)
+            if (a.mload) atomicAdd(a.mload + e.y, (u64)((e.x >> 19) & 127u));   // repartition estimate: k-mers per minimizer
             s_ev[q].y = p | (atomicAdd(&s_hist[p], 1u) << 16);
             atomicAdd(&s_kc[p], (e.x >> 19) & 127u);
           }

@@ -195,6 +195,9 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
       for (; q + 2 <= s0 + n; q += 2) {
         const Ev e0 = x.ev[q], e1 = x.ev[q + 1];
         const u32 p0 = __ldg(a.repart + e0.y), p1 = __ldg(a.repart + e1.y);     // Repartitor, PartiInfo.hpp:381
+        if (a.mload) {                                  // repartition estimate: k-mers per minimizer
+          atomicAdd(a.mload + e0.y, (u64)((e0.x >> 19) & 127u)); atomicAdd(a.mload + e1.y, (u64)((e1.x >> 19) & 127u));
+        }
         x.ev[q].y = p0 | (atomicAdd(&x.hist[p0], 1u) << 16);
         x.ev[q + 1].y = p1 | (atomicAdd(&x.hist[p1], 1u) << 16);
         atomicAdd(&x.kc[p0], (e0.x >> 19) & 127u);
@@ -203,6 +206,7 @@ s1_superk_v5(const S1Args a, const Geo geo, const S1Idx ix)
       if (q < s0 + n) {
         const Ev e0 = x.ev[q];
         const u32 p0 = __ldg(a.repart + e0.y);
+        if (a.mload) atomicAdd(a.mload + e0.y, (u64)((e0.x >> 19) & 127u));
         x.ev[q].y = p0 | (atomicAdd(&x.hist[p0], 1u) << 16);
         atomicAdd(&x.kc[p0], (e0.x >> 19) & 127u);
       }

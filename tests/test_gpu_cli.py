@@ -198,3 +198,32 @@ def test_two_gpus_from_the_command_line(workdir):
         subprocess.run([KMX] + common + ["--run-dir", f"{d}/kmx_{tag}", "--devices", "0-1", "--threads", "2"], check=True)
         for sub in ("matrices", "merge_infos", "partition_infos", "counts"):
             same_files(f"{d}/ref_{tag}", f"{d}/kmx_{tag}", sub)
+
+
+def test_balanced_repartition_is_consumed_by_the_reference(workdir):
+    """--balanced-repart: minimizer loads estimated on the device from the head of the samples, minimizers assigned heaviest
+    first to the lightest partition, repartition.minimRepart written in the reference's format.  The reference run with
+    --repart-from that directory gives the same counts / matrices / .pinfo, and the partitions are better balanced than
+    with the static (hash) map."""
+    import numpy as np
+    d = workdir
+    with open(f"{d}/fof4b.txt", "w") as f:
+        for line in open(f"{d}/fof.txt"):
+            if line.startswith("S"):
+                f.write(line)
+    common = ["pipeline", "--file", f"{d}/fof4b.txt", "--nb-partitions", "8", "--minimizer-size", "10", "--keep-tmp", "--kmer-size", "31",
+              "--mode", "kmer:count:bin", "--hard-min", "2"]
+    subprocess.run([KMX] + common + ["--run-dir", f"{d}/kmx_bal", "--balanced-repart", "--threads", "2"], check=True)
+    subprocess.run([KMX] + common + ["--run-dir", f"{d}/kmx_sta", "--static-repart", "--threads", "2"], check=True)
+    subprocess.run([REF] + common + ["--run-dir", f"{d}/ref_bal", "--repart-from", f"{d}/kmx_bal", "-t", "4"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for sub in ("matrices", "merge_infos", "partition_infos", "counts"):
+        same_files(f"{d}/ref_bal", f"{d}/kmx_bal", sub)
+
+    def imbalance(run):
+        tot = np.zeros(8)
+        for n in os.listdir(f"{run}/partition_infos"):
+            tot += np.array([int(x) for x in open(f"{run}/partition_infos/{n}").read().split()], dtype=float)
+        return tot.max() / tot.mean()
+    bal, sta = imbalance(f"{d}/kmx_bal"), imbalance(f"{d}/kmx_sta")
+    assert bal < 1.05 and bal <= sta, (bal, sta)

@@ -101,8 +101,9 @@ Options parse(int argc, char** argv)
   if (o.fof.empty() || o.dir.empty()) usage("--file and --run-dir are required");
   if (o.P == 0) usage("--nb-partitions is required (the repartition map must be fixed, SURVEY F9)");
   std::stringstream ss(o.mode); std::getline(ss, o.key_kind, ':'); std::getline(ss, o.what, ':'); std::getline(ss, o.fmt, ':');
-  if ((o.key_kind != "kmer" && o.key_kind != "hash") || (o.what != "count" && o.what != "pa" && o.what != "bf" && o.what != "bft") || (o.fmt != "bin" && !o.fmt.empty()))
-    usage("--mode must be <kmer|hash>:<count|pa|bf|bft>:bin");
+  if ((o.key_kind != "kmer" && o.key_kind != "hash") || (o.what != "count" && o.what != "pa" && o.what != "bf" && o.what != "bft") || (o.fmt != "bin" && o.fmt != "text" && !o.fmt.empty()))
+    usage("--mode must be <kmer|hash>:<count|pa|bf|bft>:<bin|text>");
+  if (o.fmt == "text" && o.what != "count" && o.what != "pa") usage("text output exists for count and pa matrices (merge.hpp:288-316,531-573)");
   if ((o.what == "bf" || o.what == "bft") && o.key_kind != "hash") usage("bf/bft need hash keys");
   if (o.until != "all" && o.until != "superk" && o.until != "count" && o.until != "merge") usage("--until must be all|superk|count|merge");
   if (o.devices.empty()) o.devices.push_back(o.device);
@@ -513,6 +514,26 @@ void merge_partitions(Run& R, const Rank& rk, PluginHost& plug, const std::vecto
         out.swap(t);
       }
     }
+    if (o.fmt == "text") {                                 // write_as_text / write_as_pa_text (merge.hpp:288-316,531-573): no header, one row per line
+      const size_t rb = 8 * kw + (fmt == KMX_FMT_COUNT ? 4 * (size_t)N : nbytes);
+      const size_t nrows = rb ? job.body.size() / rb : 0;
+      std::string txt; txt.reserve(nrows * (o.k + 2 * (size_t)N + 2));
+      std::string km(o.k, 'A');
+      for (size_t i = 0; i < nrows; i++) {
+        const uint8_t* row = &job.body[i * rb];
+        uint64_t kbuf[2] = {0, 0}; memcpy(kbuf, row, 8 * kw);
+        if (hash) txt += std::to_string(kbuf[0]);
+        else {                                             // Kmer::to_string (kmer.hpp:541-550): first base most significant, "ACTG"[code]
+          for (uint32_t b = 0; b < o.k; b++) km[o.k - 1 - b] = "ACTG"[(kbuf[b >> 5] >> (2 * (b & 31))) & 3];
+          txt += km;
+        }
+        if (fmt == KMX_FMT_COUNT) { uint32_t c; for (uint32_t s2 = 0; s2 < N; s2++) { memcpy(&c, row + 8 * kw + 4 * s2, 4); txt += ' '; txt += std::to_string(c); } }
+        else for (uint32_t s2 = 0; s2 < N; s2++) { txt += ' '; txt += ((row[8 * kw + (s2 >> 3)] >> (s2 & 7)) & 1) ? '1' : '0'; }
+        txt += '\n';
+      }
+      job.path += ".txt"; job.head.clear();
+      job.body.assign(txt.begin(), txt.end());
+    }
     if (fmt == KMX_FMT_BFT && !bf_fds.empty()) {           // per-sample filter: row s of this partition at its place in filters/<id>.bf
       const size_t rb = W / 8;
       for (uint32_t s2 = 0; s2 < N; s2++)
@@ -585,7 +606,7 @@ int main(int argc, char** argv)
       op << "Options: dir=" << o.dir << ", nb_threads=" << o.threads << ", fof=" << o.fof << ", kmer_size=" << o.k << ", c_ab_min=" << o.hard_min
          << ", m_ab_min=" << o.soft_min << ", r_min=" << o.rec_min << ", save_if=" << o.share_min << ", minim_size=" << o.m << ", nb_parts=" << P
          << ", bloom_size=" << o.bloom << ", keep_tmp=" << o.keep_tmp << ", static_repart=" << o.static_repart << ", use_plugin=" << !o.plugin.empty()
-         << ", plugin=" << o.plugin << ", plugin_config=" << o.plugin_config << ", mode=" << o.what << ", format=bin, count_format=" << o.key_kind
+         << ", plugin=" << o.plugin << ", plugin_config=" << o.plugin_config << ", mode=" << o.what << ", format=" << (o.fmt == "text" ? "text" : "bin") << ", count_format=" << o.key_kind
          << ", until=" << o.until << ", engine=kmx_sm100, gpus=" << G << "\n";
     }
     { std::string h; put<uint64_t>(h, W * P); put<uint64_t>(h, P); put<uint64_t>(h, W); put<uint64_t>(h, W / 8); put<uint32_t>(h, o.m); write_file(o.dir + "/hash.info", h, nullptr, 0); }

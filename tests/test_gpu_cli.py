@@ -227,3 +227,15 @@ def test_balanced_repartition_is_consumed_by_the_reference(workdir):
         return tot.max() / tot.mean()
     bal, sta = imbalance(f"{d}/kmx_bal"), imbalance(f"{d}/kmx_sta")
     assert bal < 1.05 and bal <= sta, (bal, sta)
+
+
+@pytest.mark.parametrize("tag,args", [
+    ("txt_kmer_count", ["--kmer-size", "31", "--mode", "kmer:count:text", "--hard-min", "2"]),
+    ("txt_k63_pa", ["--kmer-size", "63", "--mode", "kmer:pa:text", "--hard-min", "1", "--soft-min", "2", "--recurrence-min", "2"]),
+    ("txt_hash_count", ["--kmer-size", "31", "--mode", "hash:count:text", "--hard-min", "2", "--bloom-size", "2000000"]),
+])
+def test_text_matrices(workdir, tag, args):
+    """<kmer|hash>:<count|pa>:text (write_as_text / write_as_pa_text, merge.hpp:288-316,531-573): matrix_P.<ext>.txt byte for byte."""
+    a, b = run_both(workdir, tag, args)
+    same_files(a, b, "matrices")
+    same_files(a, b, "merge_infos")

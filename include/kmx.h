@@ -114,6 +114,12 @@ int kmx_lane_superk_push_fastq(kmx_ctx* ctx, uint32_t lane, const char* text, si
 int kmx_lane_superk_push_reads(kmx_ctx* ctx, uint32_t lane, const char* seqs, const uint64_t* off, size_t nseq);
 int kmx_lane_superk_end(kmx_ctx* ctx, uint32_t lane, uint64_t* kmers_per_partition);
 int kmx_lane_count_sample(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min);
+/* kmx_lane_count_sample + the sample's abundance histogram (--hist: KHist, histogram.hpp:34-207; every distinct key of the
+ * sample is binned BEFORE the hard-min test, count_processor.hpp:61-70,135-146).
+ * out = [uniq, total, oob_lower_unique, oob_lower_total, oob_upper_unique, oob_upper_total,
+ *        hist_unique[upper-lower+1], hist_total[upper-lower+1]]  (the reference uses lower 1, upper 255).               */
+int kmx_lane_count_sample_hist(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min, uint32_t lower, uint32_t upper,
+                               uint64_t* out);
 /* size of / copy out one list == body of counts/partition_P/<id>.kmer|.hash
  * keys: n*w u64 (w = 1 for hash keys), counts: n u32.                                        */
 int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n);

@@ -57,6 +57,7 @@ SYMBOLS = {
     "kmx_lane_superk_push_reads": (_i, [_vp, _u32, _vp, _vp, _sz]),
     "kmx_lane_superk_end": (_i, [_vp, _u32, C.POINTER(_u64)]),
     "kmx_lane_count_sample": (_i, [_vp, _u32, _u32, _u32]),
+    "kmx_lane_count_sample_hist": (_i, [_vp, _u32, _u32, _u32, _u32, _u32, _vp]),
     "kmx_dist_run_samples": (_i, [_vp, _u32, C.POINTER(C.c_void_p), C.POINTER(_sz), _i, C.POINTER(_u32), C.POINTER(_u64)]),
     "kmx_counts_size": (_i, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "kmx_counts_get": (_i, [_vp, _u32, _u32, _vp, _vp]),

@@ -43,7 +43,7 @@ struct Options {
   std::string fof, dir, mode = "kmer:count:bin", repart_from, until = "all", plugin, plugin_config;
   uint32_t k = 31, m = 10, P = 0, hard_min = 2, soft_min = 1, rec_min = 1, share_min = 0, threads = 4;
   uint64_t bloom = 10000000;
-  bool keep_tmp = false, static_repart = true, balanced_repart = false;
+  bool keep_tmp = false, static_repart = true, balanced_repart = false, hist = false;
   size_t repart_sample_mib = 64;     // --balanced-repart: text sampled from the head of each of up to 16 samples
   int device = 0;
   std::vector<int> devices;          // --devices a-b | a,b,c : partitions sharded over these GPUs (one in-process rank per GPU)
@@ -57,7 +57,7 @@ struct Options {
   std::cerr << "usage: kmx pipeline --file <fof> --run-dir <dir> --nb-partitions <P> [--kmer-size 31]\n"
                "           [--mode <kmer|hash>:<count|pa|bf|bft>:bin] [--hard-min 2] [--soft-min 1] [--recurrence-min 1]\n"
                "           [--share-min 0] [--minimizer-size 10] [--bloom-size 10000000] [--static-repart | --repart-from <run-dir> | --balanced-repart]\n"
-               "           [--until all|superk|count|merge] [--keep-tmp] [--threads 4] [--plugin lib.so [--plugin-config s]] [--device 0 | --devices 0-7] [--block-mib 256]\n";
+               "           [--until all|superk|count|merge] [--keep-tmp] [--hist] [--threads 4] [--plugin lib.so [--plugin-config s]] [--device 0 | --devices 0-7] [--block-mib 256]\n";
   std::exit(why ? EXIT_FAILURE : EXIT_SUCCESS);
 }
 
@@ -85,6 +85,7 @@ Options parse(int argc, char** argv)
     else if (a == "--repart-from") { o.repart_from = need(i); o.static_repart = false; }
     else if (a == "--until") o.until = need(i);
     else if (a == "--keep-tmp") o.keep_tmp = true;
+    else if (a == "--hist") o.hist = true;
     else if (a == "--threads" || a == "-t") o.threads = std::stoul(need(i));
     else if (a == "--plugin") o.plugin = need(i);
     else if (a == "--plugin-config") o.plugin_config = need(i);
@@ -420,7 +421,17 @@ void process_sample(Run& R, kmx_ctx* ctx, uint32_t lane, uint32_t s, char* pin, 
     for (const std::string& f : smp.files) push_parsed(ctx, lane, f);
   }
   KX(kmx_lane_superk_end(ctx, lane, R.pinfo[s].data()));
-  if (R.o.until != "superk") KX(kmx_lane_count_sample(ctx, lane, s, R.hard_min(s)));
+  if (R.o.until == "superk") return;
+  if (!R.o.hist) { KX(kmx_lane_count_sample(ctx, lane, s, R.hard_min(s))); return; }
+  // --hist: histograms/<id>.hist (HistWriter, io/hist_file.hpp:31-130; KHist(i, k, 1, 255), task_scheduler.hpp:103)
+  const uint64_t lower = 1, upper = 255, nb = upper - lower + 1;
+  std::vector<uint64_t> hv(6 + 2 * nb);
+  KX(kmx_lane_count_sample_hist(ctx, lane, s, R.hard_min(s), (uint32_t)lower, (uint32_t)upper, hv.data()));
+  std::string h = km_header();
+  put<uint64_t>(h, 0x747369686bULL); put<uint32_t>(h, R.o.k); put<uint32_t>(h, s); put<uint64_t>(h, lower); put<uint64_t>(h, upper);
+  put<uint64_t>(h, hv[0]); put<uint64_t>(h, hv[1]);                       // uniq, total
+  put<uint64_t>(h, hv[3]); put<uint64_t>(h, hv[2]); put<uint64_t>(h, hv[5]); put<uint64_t>(h, hv[4]);   // oob_ln, oob_lu, oob_un, oob_uu (the order serialize() writes them in)
+  write_file(R.o.dir + "/histograms/" + smp.id + ".hist", h, hv.data() + 6, 2 * nb * 8);
 }
 
 std::string matrix_header(const Run& R, uint32_t p)
@@ -665,6 +676,7 @@ int main(int argc, char** argv)
       // one in-process rank per GPU: rank g parses the samples [g nl, (g+1) nl), the buckets travel to the partitions' owners
       // (one NCCL all-to-all-v per sample), every rank counts and later merges its own partitions.  Batches of a few samples.
       if (o.until == "superk") throw Error("--until superk needs a single --device");
+      if (o.hist) throw Error("--hist needs a single --device");
       const uint32_t nl = (N + G - 1) / G, B = std::max(lanes, 4u);
       std::vector<uint8_t> ids((size_t)128 * lanes);
       for (uint32_t t = 0; t < lanes; t++) if (kmx_dist_unique_id(&ids[(size_t)128 * t])) throw Error("kmx_dist_unique_id failed (libnccl.so.2 not loadable?)");

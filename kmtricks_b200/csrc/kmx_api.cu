@@ -89,6 +89,9 @@ struct Lane {
   char* h_pin = nullptr; size_t h_pin_cap = 0;     // pinned scratch for small read-backs
   // ---- stage 2
   DBuf hist, sub_counts, sub_off, bitmap;
+  std::vector<ArenaBlock> sarena;  // lists of a pass whose output is thrown away (the all-keys pass behind --hist)
+  bool to_scratch = false;
+  DBuf hist_dev;                   // histogram pass: list table + counters
   DBuf binbuf, binmeta;            // binned hash counting: 16-bit slot offsets per (window, bin) + cursors / look-back words / layout
   u64 d_est = 0;                   // expected surviving (key,count) pairs per sample (grows with what was seen)
   DBuf keys_lo, keys_hi, keys_lo2, keys_hi2, sort_work, tmp_cnt, ht_keys, ht_cnts;
@@ -247,6 +250,21 @@ static cudaError_t arena_alloc(kmx_ctx* ctx, size_t bytes, void** out)
   *out = nb.p;
   return cudaSuccess;
 }
+// output space of a counting pass: the context's arena (lists that stay), or the lane's scratch blocks
+static cudaError_t list_alloc(Lane* ln, size_t bytes, void** out)
+{
+  if (!ln->to_scratch) return arena_alloc(ln->ctx, bytes, out);
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  for (auto& b : ln->sarena) if (b.cap - b.used >= bytes) { *out = b.p + b.used; b.used += bytes; return cudaSuccess; }
+  ArenaBlock nb; nb.cap = std::max(bytes, (size_t)64 << 20); nb.used = bytes;
+  cudaError_t e = cudaMalloc((void**)&nb.p, nb.cap);
+  if (e != cudaSuccess) return e;
+  add_bytes(ln->ctx, (long long)nb.cap);
+  ln->sarena.push_back(nb);
+  *out = nb.p;
+  return cudaSuccess;
+}
 static void arena_clear(kmx_ctx* ctx)
 {
   for (auto& b : ctx->arena) { cudaFree(b.p); ctx->dev_bytes -= b.cap; }
@@ -282,6 +300,9 @@ static void lane_destroy(Lane* ln)
   DBuf* bufs[] = {&ln->text, &ln->seq_start, &ln->seq_len, &ln->tile_counts, &ln->tile_prefix, &ln->nlmask, &ln->records, &ln->hist, &ln->binbuf, &ln->binmeta,
                   &ln->sub_counts, &ln->sub_off, &ln->bitmap, &ln->cta_tile, &ln->keys_lo, &ln->keys_hi, &ln->keys_lo2, &ln->keys_hi2, &ln->sort_work, &ln->tmp_cnt, &ln->ht_keys, &ln->ht_cnts};
   for (DBuf* b : bufs) release(ctx, *b);
+  release(ctx, ln->hist_dev);
+  for (auto& b : ln->sarena) { cudaFree(b.p); add_bytes(ctx, -(long long)b.cap); }
+  ln->sarena.clear();
   void* singles[] = {ln->d_total, ln->d_flags, ln->d_boff, ln->d_bcap, ln->d_cursor, ln->d_kcnt};
   for (void* p : singles) if (p) cudaFree(p);
   if (ln->h_pin) cudaFreeHost(ln->h_pin);
@@ -710,8 +731,8 @@ static int count_hash_hist(Lane* ln, uint32_t sample, uint32_t hard_min, const u
   u64 cap = std::max<u64>(4096, ln->d_est);
   for (int attempt = 0; attempt < 4; attempt++) {
     void* kp = nullptr; void* cp = nullptr;
-    CK(arena_alloc(ctx, cap * 8, &kp));
-    CK(arena_alloc(ctx, cap * 4, &cp));
+    CK(list_alloc(ln, cap * 8, &kp));
+    CK(list_alloc(ln, cap * 4, &cp));
     u64* hm = (u64*)(ln->h_pin + (size_t)P * 8);             // staging for meta = {cursor, cursor', capacity, -} + flags
     hm[0] = 0; hm[1] = 0; hm[2] = cap; hm[3] = 0; hm[4] = 0;
     { SmallCopyBatch b(ln); b.add(d_meta, hm, 40); CK(b.go()); }            // meta[4] + flags[2]
@@ -804,8 +825,8 @@ static int count_hash_binned(Lane* ln, uint32_t sample, uint32_t hard_min, const
     CK(ensure(ln, ln->binmeta, zbytes + up_bytes + (size_t)P * 8 + 64));
     char* dm = (char*)ln->binmeta.p;
     void* kp = nullptr; void* cp = nullptr;
-    CK(arena_alloc(ctx, cap * 8, &kp));
-    CK(arena_alloc(ctx, cap * 4, &cp));
+    CK(list_alloc(ln, cap * 8, &kp));
+    CK(list_alloc(ln, cap * 4, &cp));
     HashBinArgs a;
     a.records = ln->records.p; a.boff = ln->d_boff; a.bcnt = ln->d_cursor;
     a.k = (int)ctx->prm.kmer_size; a.nwin = P; a.Wbits = Wb; a.NB = NB; a.bs_log = bs_log;
@@ -932,6 +953,84 @@ extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* text
   return first_err.load();
 }
 
+// ---- k-mer abundance histogram of a sample (--hist; KHist::inc is called for EVERY distinct key, before the hard-min
+// test: count_processor.hpp:61-70,135-146, histogram.hpp:52-71).  The survivor lists do not hold the keys below hard-min, so
+// the sample is first counted with hard-min 1 into lane scratch (all distinct keys), a kernel bins the counts, the scratch is
+// dropped, and the sample is counted again with its real hard-min.  A side output, not on the timed path.
+static const u32 KMX_HIST_MAXBINS = 1024;
+__global__ void __launch_bounds__(256) count_hist_kernel(const MergeList* __restrict__ lists, u32 lower, u32 upper, u64* __restrict__ out)
+{
+  __shared__ u32 s_u[KMX_HIST_MAXBINS];
+  __shared__ unsigned long long s_n[KMX_HIST_MAXBINS], s_acc[6];
+  const u32 nb = upper - lower + 1u;
+  for (u32 i = threadIdx.x; i < nb; i += 256) { s_u[i] = 0; s_n[i] = 0; }
+  if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
+  __syncthreads();
+  const MergeList L = lists[blockIdx.y];
+  unsigned long long a[6] = {0, 0, 0, 0, 0, 0};            // uniq, total, oob_lu, oob_ln, oob_uu, oob_un
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < L.n; i += (u64)gridDim.x * 256) {
+    const u32 c = L.cnt[i];
+    a[0]++; a[1] += c;
+    if (c < lower) { a[2]++; a[3] += c; }
+    else if (c > upper) { a[4]++; a[5] += c; }
+    else { atomicAdd(&s_u[c - lower], 1u); atomicAdd(&s_n[c - lower], (unsigned long long)c); }
+  }
+  for (int q = 0; q < 6; q++) if (a[q]) atomicAdd(&s_acc[q], a[q]);
+  __syncthreads();
+  if (threadIdx.x < 6 && s_acc[threadIdx.x]) atomicAdd((unsigned long long*)out + threadIdx.x, s_acc[threadIdx.x]);
+  for (u32 i = threadIdx.x; i < nb; i += 256) {
+    if (s_u[i]) atomicAdd((unsigned long long*)out + 6 + i, (unsigned long long)s_u[i]);
+    if (s_n[i]) atomicAdd((unsigned long long*)out + 6 + nb + i, s_n[i]);
+  }
+}
+
+static int count_sample_hist(Lane* ln, uint32_t sample, uint32_t hard_min, uint32_t lower, uint32_t upper, uint64_t* out)
+{
+  kmx_ctx* ctx = ln->ctx;
+  const u32 P = ctx->prm.nb_partitions;
+  if (!out || lower < 1 || upper < lower || upper - lower + 1 > KMX_HIST_MAXBINS) return fail(ln, KMX_ERR_ARG, "histogram range [%u, %u] unsupported (1 <= lower <= upper, at most %u bins)", lower, upper, KMX_HIST_MAXBINS);
+  if (sample >= ctx->prm.nb_samples) return fail(ln, KMX_ERR_ARG, "sample %u >= nb_samples", sample);
+  const u32 nb = upper - lower + 1u;
+  const bool one_pass = hard_min <= 1;                       // the lists already hold every distinct key
+  ln->to_scratch = !one_pass;
+  const u64 d_est0 = ln->d_est;
+  int rc = count_sample(ln, sample, 1);
+  ln->to_scratch = false;
+  if (!one_pass) ln->d_est = d_est0;                         // the all-keys pass must not inflate the output estimate of the real passes
+  if (!rc) {
+    const size_t tab = (size_t)P * sizeof(MergeList), nout = (size_t)(6 + 2 * nb) * 8;
+    cudaError_t e = ensure(ln, ln->hist_dev, tab + nout);
+    if (e == cudaSuccess) e = ensure_pin(ln, std::max(tab, nout) + 256);
+    if (e != cudaSuccess) rc = fail(ln, KMX_ERR_NOMEM, "histogram buffers: %s", cudaGetErrorString(e));
+    if (!rc) {
+      MergeList* hl = (MergeList*)ln->h_pin;
+      u64 max_n = 0;
+      for (u32 p = 0; p < P; p++) { const ListRef& L = ctx->lists[(size_t)sample * P + p]; hl[p].lo = L.lo; hl[p].hi = L.hi; hl[p].cnt = L.cnt; hl[p].n = L.n; max_n = std::max(max_n, L.n); }
+      u64* d_out = (u64*)((char*)ln->hist_dev.p + tab);
+      SmallCopyBatch b(ln); b.add(ln->hist_dev.p, hl, tab);
+      e = b.go();
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, nout, ln->st);
+      if (e == cudaSuccess && max_n) {
+        const unsigned gx = (unsigned)std::min<u64>(64, (max_n + 255) / 256);
+        count_hist_kernel<<<dim3(gx, P), 256, 0, ln->st>>>((const MergeList*)ln->hist_dev.p, lower, upper, d_out);
+        ln->launches += 1;
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ln->st);              // the table staging is free again
+      if (e == cudaSuccess) { SmallCopyBatch b2(ln); b2.add(ln->h_pin, d_out, nout); e = b2.go(); }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ln->st);
+      if (e != cudaSuccess) rc = fail(ln, KMX_ERR_CUDA, "histogram pass: %s", cudaGetErrorString(e));
+      else memcpy(out, ln->h_pin, nout);
+    }
+  }
+  for (auto& b : ln->sarena) b.used = 0;                     // the all-keys lists are dropped (their blocks are kept for the next sample)
+  if (!one_pass) {
+    for (u32 p = 0; p < P; p++) ctx->lists[(size_t)sample * P + p] = ListRef();
+    if (!rc) rc = count_sample(ln, sample, hard_min);
+  }
+  return rc;
+}
+
 // ---- lane-addressed entry points (one host thread per lane)
 extern "C" int kmx_lanes(kmx_ctx* ctx, uint32_t n)
 {
@@ -961,6 +1060,12 @@ extern "C" int kmx_lane_superk_push_reads(kmx_ctx* ctx, uint32_t lane, const cha
 }
 extern "C" int kmx_lane_superk_end(kmx_ctx* ctx, uint32_t lane, uint64_t* kmers_per_partition) { LANE_N(lane); return superk_end(ln, kmers_per_partition); }
 extern "C" int kmx_lane_count_sample(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min) { LANE_N(lane); return count_sample(ln, sample, hard_min); }
+extern "C" int kmx_lane_count_sample_hist(kmx_ctx* ctx, uint32_t lane, uint32_t sample, uint32_t hard_min, uint32_t lower, uint32_t upper, uint64_t* out)
+{
+  LANE_N(lane);
+  if (!ln->sample_ready) return fail(ln, KMX_ERR_STATE, "kmx_lane_count_sample_hist needs a sample finished by kmx_lane_superk_end");
+  return count_sample_hist(ln, sample, hard_min, lower, upper, out);
+}
 
 extern "C" int kmx_counts_size(kmx_ctx* ctx, uint32_t sample, uint32_t partition, uint64_t* n)
 {

@@ -40,9 +40,9 @@ static int count_generic(Lane* ln, uint32_t sample, uint32_t hard_min)
   CK(rle_segments(P, koff.data(), slo, shi, KW, hard_min, ln->sort_work.p, toff, soff, 0, nullptr, nullptr, nullptr, ln->st, &ln->launches));
   const u64 D = soff[P];
   void *kp = nullptr, *hp = nullptr, *cp = nullptr;
-  CK(arena_alloc(ctx, D * 8, &kp));
-  if (KW == 2) CK(arena_alloc(ctx, D * 8, &hp));
-  CK(arena_alloc(ctx, D * 4, &cp));
+  CK(list_alloc(ln, D * 8, &kp));
+  if (KW == 2) CK(list_alloc(ln, D * 8, &hp));
+  CK(list_alloc(ln, D * 4, &cp));
   CK(rle_segments(P, koff.data(), slo, shi, KW, hard_min, ln->sort_work.p, toff, soff, 1, (u64*)kp, (u64*)hp, (u32*)cp, ln->st, &ln->launches));
   for (u32 p = 0; p < P; p++) {
     ListRef& L = ctx->lists[(size_t)sample * P + p];
@@ -117,9 +117,9 @@ static int count_kmer_ht(Lane* ln, uint32_t sample, uint32_t hard_min)
     CK(segmented_radix_sort(P, sb.data(), se.data(), (u64*)ln->keys_lo.p, KW == 2 ? (u64*)ln->keys_hi.p : nullptr, (u64*)ln->keys_lo2.p,
                             KW == 2 ? (u64*)ln->keys_hi2.p : nullptr, KW, 0, 2 * (int)ctx->prm.kmer_size, ln->sort_work.p, &in_alt, ln->st, &ln->launches)); }
   void *kp = nullptr, *khp = nullptr, *cp = nullptr;
-  CK(arena_alloc(ctx, D * 8, &kp));
-  if (KW == 2) CK(arena_alloc(ctx, D * 8, &khp));
-  CK(arena_alloc(ctx, D * 4, &cp));
+  CK(list_alloc(ln, D * 8, &kp));
+  if (KW == 2) CK(list_alloc(ln, D * 8, &khp));
+  CK(list_alloc(ln, D * 4, &cp));
   memcpy(hp, oo.data(), P * 8);
   CK(cudaMemcpyAsync(d_oo, hp, (size_t)P * 8, cudaMemcpyHostToDevice, ln->st));
   { PROF(KMX_PROF_RLE);

@@ -239,3 +239,17 @@ def test_text_matrices(workdir, tag, args):
     a, b = run_both(workdir, tag, args)
     same_files(a, b, "matrices")
     same_files(a, b, "merge_infos")
+
+
+@pytest.mark.parametrize("tag,args", [
+    ("hist_kmer", ["--kmer-size", "31", "--mode", "kmer:count:bin", "--hard-min", "3", "--hist"]),
+    ("hist_hash", ["--kmer-size", "31", "--mode", "hash:count:bin", "--hard-min", "2", "--bloom-size", "2000000", "--hist"]),
+    ("hist_k63", ["--kmer-size", "63", "--mode", "kmer:pa:bin", "--hard-min", "1", "--hist"]),
+])
+def test_abundance_histograms(workdir, tag, args):
+    """--hist: histograms/<id>.hist (every distinct key of the sample binned before the hard-min test, lower 1, upper 255,
+    histogram.hpp:34-207 + io/hist_file.hpp) byte for byte, and the matrices stay what they are without --hist."""
+    a, b = run_both(workdir, tag, args)
+    same_files(a, b, "histograms")
+    same_files(a, b, "matrices")
+    same_files(a, b, "counts")

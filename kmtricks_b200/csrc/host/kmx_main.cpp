@@ -639,6 +639,31 @@ int main(int argc, char** argv)
       std::ofstream out(o.dir + "/repartition_gatb/repartition.minimRepart", std::ios::binary);
       out.write(h.data(), h.size()); out.write((const char*)table.data(), tn * 2); out.write(tail.data(), tail.size()); }
 
+    if (o.m <= 12) {   // minimizers/minimizers.P (RepartTask::postprocess, task.hpp:160-168; Repartition::write_minimizers, repartition.hpp:116-124)
+      std::vector<std::string> buf(P);
+      std::string mm(o.m, 'A');
+      for (size_t x = 0; x < tn; x++) {
+        for (uint32_t b = 0; b < o.m; b++) mm[o.m - 1 - b] = "ACTG"[(x >> (2 * b)) & 3];      // Mmer::to_string (kmer.hpp:115-128)
+        buf[table[x]] += mm; buf[table[x]] += '\n';
+      }
+      for (uint32_t p = 0; p < P; p++) write_file(o.dir + "/minimizers/minimizers." + std::to_string(p), buf[p], nullptr, 0);
+    }
+    {   // config_gatb/gatb.config: the fields Configuration::save writes, in its order (gatb Configuration.cpp:145-178).  The reference reads
+        // k, m and the partition count back from it when this directory is given to --repart-from (check_repart_compatibility,
+        // task.hpp:135-147); the estimates (sequence counts, volumes) are GATB planning figures nothing downstream reads: zero here.
+      std::string c;
+      put<uint64_t>(c, o.k); put<uint64_t>(c, o.m); put<uint64_t>(c, 0); put<uint64_t>(c, 0);   // _kmerSize, _minim_size, _repartitionType, _minimizerType
+      put<uint64_t>(c, 0); put<uint32_t>(c, 8000);                                              // _max_disk_space, _max_memory
+      put<uint64_t>(c, 1); put<uint64_t>(c, 1); put<uint64_t>(c, 1); put<uint64_t>(c, 1);       // _nbCores, _nb_partitions_in_parallel, _abundanceUserNb, _nbCores_per_partition
+      for (int q = 0; q < 6; q++) put<uint64_t>(c, 0);                                          // _estimateSeqNb/TotalSize/MaxSize, _available_space, _volume, _kmersNb
+      put<uint32_t>(c, 1); put<uint32_t>(c, P); put<uint16_t>(c, (uint16_t)(64 * ((o.k + 31) / 32))); put<uint16_t>(c, 1); put<uint32_t>(c, 0);   // _nb_passes, _nb_partitions, _nb_bits_per_kmer, _nb_banks, _nb_cached_items_per_core_per_part
+      write_file(o.dir + "/config_gatb/gatb.config", c, nullptr, 0);
+    }
+    {
+      std::ofstream bi(o.dir + "/build_infos.txt");
+      bi << "kmx (kmtricks hot path on sm_100a; run-directory layout of kmtricks v1.6.0)\n\n- BUILD -\nkmer: 32,64\nmax_c: 4294967295\nengine: libkmx_sm100\n";
+    }
+
     kmx_params prm{};
     prm.kmer_size = o.k; prm.minim_size = o.m; prm.nb_partitions = P; prm.key_kind = hash ? KMX_KEY_HASH : KMX_KEY_KMER;
     prm.window_bits = hash ? W : 0; prm.repart_table = table.data(); prm.nb_samples = N;

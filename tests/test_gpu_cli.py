@@ -64,9 +64,11 @@ def same_files(a, b, sub, must_exist=True):
 ])
 def test_run_dir_equals_reference(workdir, tag, args):
     a, b = run_both(workdir, tag, args)
-    for sub in ("matrices", "merge_infos", "partition_infos", "counts", "repartition_gatb"):
+    for sub in ("matrices", "merge_infos", "partition_infos", "counts", "repartition_gatb", "minimizers"):
         same_files(a, b, sub)
     assert filecmp.cmp(f"{a}/hash.info", f"{b}/hash.info", shallow=False)
+    ca, cb = open(f"{a}/config_gatb/gatb.config", "rb").read(), open(f"{b}/config_gatb/gatb.config", "rb").read()
+    assert len(ca) == len(cb) == 140 and ca[:32] == cb[:32] and ca[124:136] == cb[124:136]      # k, m, types; passes, partitions, bits per k-mer, banks
     if tag == "hash_bf":
         same_files(a, b, "fpr")
 

@@ -656,7 +656,9 @@ int main(int argc, char** argv)
       put<uint64_t>(c, 0); put<uint32_t>(c, 8000);                                              // _max_disk_space, _max_memory
       put<uint64_t>(c, 1); put<uint64_t>(c, 1); put<uint64_t>(c, 1); put<uint64_t>(c, 1);       // _nbCores, _nb_partitions_in_parallel, _abundanceUserNb, _nbCores_per_partition
       for (int q = 0; q < 6; q++) put<uint64_t>(c, 0);                                          // _estimateSeqNb/TotalSize/MaxSize, _available_space, _volume, _kmersNb
-      put<uint32_t>(c, 1); put<uint32_t>(c, P); put<uint16_t>(c, (uint16_t)(64 * ((o.k + 31) / 32))); put<uint16_t>(c, 1); put<uint32_t>(c, 0);   // _nb_passes, _nb_partitions, _nb_bits_per_kmer, _nb_banks, _nb_cached_items_per_core_per_part
+      put<uint32_t>(c, 1); put<uint32_t>(c, P); put<uint16_t>(c, (uint16_t)(64 * ((o.k + 31) / 32)));
+      size_t nfiles = 0; for (const Sample& sm : R.samples) nfiles += sm.files.size();
+      put<uint16_t>(c, (uint16_t)nfiles); put<uint32_t>(c, 0);   // _nb_passes, _nb_partitions, _nb_bits_per_kmer, _nb_banks, _nb_cached_items_per_core_per_part
       write_file(o.dir + "/config_gatb/gatb.config", c, nullptr, 0);
     }
     {

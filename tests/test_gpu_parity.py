@@ -17,6 +17,11 @@ CASES = {
     "k63_kmer_count": dict(k=63, P=4, mode="kmer:count:bin", hard_min=2),
     "k63_hash_bf": dict(k=63, P=4, mode="hash:bf:bin", hard_min=2, bloom_size=300_000),
     "k21_m8": dict(k=21, m=8, P=5, mode="kmer:count:bin", hard_min=1),
+    # hash keys at other k: the binned pass A rolls on 32-bit halves for 28 <= k <= 32 and on 64-bit words (128-bit tail) below
+    "k21_m8_hash_count": dict(k=21, m=8, P=5, mode="hash:count:bin", hard_min=1, bloom_size=300_000),
+    "k27_hash_bf": dict(k=27, P=4, mode="hash:bf:bin", hard_min=2, bloom_size=300_000),
+    "k28_hash_count": dict(k=28, P=4, mode="hash:count:bin", hard_min=2, bloom_size=300_000),
+    "k32_hash_count": dict(k=32, P=4, mode="hash:count:bin", hard_min=1, bloom_size=300_000),
     "k40_m11": dict(k=40, m=11, P=6, mode="kmer:count:bin", hard_min=2),
     "k32": dict(k=32, P=4, mode="kmer:count:bin", hard_min=1),
     "k33": dict(k=33, P=4, mode="kmer:count:bin", hard_min=1),
@@ -239,6 +244,21 @@ def test_hash_mode_larger_sample_all_paths(monkeypatch):
     monkeypatch.setenv("KMX_HIST_FUSE", "1")
     got, want = _run_both(samples, case)
     _compare(got, want, case["P"], len(samples))
+
+
+def test_hash_mode_many_bins_per_window(monkeypatch):
+    """A window of 3 M slots counted with 32-bit counters = 184 bins of 16 K slots per partition: the pass-A variant with the
+    larger per-bin arrays (more than 128 bins per window); with 16-bit counters the same window has 92 bins."""
+    from kmtricks_b200 import synth
+    samples = [[synth.make_fastq(17, s, 20000, L=150, G=150000, d=3e-3, e=3e-3, revcomp=True)] for s in range(2)]
+    case = dict(k=31, P=4, mode="hash:count:bin", hard_min=2, bloom_size=12_000_000)
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    assert got["hash_binned"] == len(samples)
+    monkeypatch.setenv("KMX_HIST32", "1")
+    got, want = _run_both(samples, case)
+    _compare(got, want, case["P"], len(samples))
+    assert got["hash_binned"] == len(samples)
 
 
 def test_hash_counter_wrap_falls_back_to_32_bit(monkeypatch):

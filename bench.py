@@ -61,7 +61,7 @@ def parse_args():
                     help="BASELINE configs 3-5 (1000 x 5M kmer:count, 1000 x 5M hash:bft, 500 x 5M k=63 kmer:pa + rescue) after the main "
                          "measurement, reported under other_configs; auto = only on 8 GPUs, where they fit at full size")
     ap.add_argument("--oc-child", default="", help=argparse.SUPPRESS)      # internal: run ONE other config in this (child) process
-    ap.add_argument("--oc-timeout-s", type=float, default=150.0, help="other_configs: hard limit per config (each runs in child processes)")
+    ap.add_argument("--oc-timeout-s", type=float, default=120.0, help="other_configs: hard limit per config (each runs in child processes)")
     ap.add_argument("--oc-samples-scale", type=float, default=1.0, help="other_configs: fraction of the samples (testing on fewer GPUs)")
     ap.add_argument("--oc-reads-scale", type=float, default=1.0, help="other_configs: fraction of the reads per sample")
     return ap.parse_args()
@@ -691,11 +691,11 @@ def main_kmx(args):
         env["TORCHELASTIC_USE_AGENT_STORE"] = "False"
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--oc-child", "parity", "--gpus", str(world)], env=env,
-                               capture_output=True, text=True, timeout=180)
+                               capture_output=True, text=True, timeout=120)
             out = [l for l in r.stdout.splitlines() if l.startswith("{")]
             parity = json.loads(out[-1])["parity_check"] if out else ("ok" if r.returncode == 0 and rank != 0 else f"error: {(r.stderr or 'no output')[-200:]}")
         except subprocess.TimeoutExpired:
-            parity = "no result within 180 s"
+            parity = "no result within 120 s"
         except Exception as e:
             parity = f"error: {e}"
         log(f"parity check: {parity}")

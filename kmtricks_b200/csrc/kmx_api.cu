@@ -108,6 +108,13 @@ struct kmx_ctx {
   std::string err;
   std::mutex mu;                   // arena, err, dev_bytes
   std::mutex lanes_mu;             // lane creation
+  // Buffers replaced by bigger ones are NOT freed on the spot: cudaFree / cudaFreeHost wait for every kernel on the device, and in
+  // a multi-GPU run another lane's NCCL kernel may be spinning for a peer whose own lane thread sits in the same kind of wait on
+  // its device -- a cycle over lanes and ranks that hung the first step at 8 GPUs.  They are freed at points where none of this
+  // context's kernels can be in flight (after all lanes were synchronised).
+  std::mutex grave_mu;
+  std::vector<std::pair<void*, size_t>> grave_dev;
+  std::vector<void*> grave_host;
   u64 dev_bytes = 0;
   std::vector<void*> user_allocs;
   int hist_ok = -1;
@@ -211,6 +218,15 @@ cudaError_t SmallCopyBatch::go()
   return cudaGetLastError();
 }
 
+static void defer_free(kmx_ctx* ctx, void* dev, size_t cap) { std::lock_guard<std::mutex> g(ctx->grave_mu); ctx->grave_dev.push_back({dev, cap}); }
+// frees what was set aside; the caller guarantees that no kernel of this context is in flight (all lanes synchronised)
+static void reap(kmx_ctx* ctx)
+{
+  std::vector<std::pair<void*, size_t>> dv; std::vector<void*> hv;
+  { std::lock_guard<std::mutex> g(ctx->grave_mu); dv.swap(ctx->grave_dev); hv.swap(ctx->grave_host); }
+  for (auto& x : dv) { cudaFree(x.first); add_bytes(ctx, -(long long)x.second); }
+  for (void* h : hv) cudaFreeHost(h);
+}
 static cudaError_t ensure(Lane* ln, DBuf& b, size_t bytes)
 {
   if (bytes <= b.cap) return cudaSuccess;
@@ -218,8 +234,14 @@ static cudaError_t ensure(Lane* ln, DBuf& b, size_t bytes)
   ncap = (ncap + 255) & ~(size_t)255;
   void* np = nullptr;
   cudaError_t e = cudaMalloc(&np, ncap);
+  if (e == cudaErrorMemoryAllocation) {            // out of memory with buffers set aside: give them back (this lane only waits for itself first)
+    cudaGetLastError();
+    cudaStreamSynchronize(ln->st);
+    reap(ln->ctx);
+    e = cudaMalloc(&np, ncap);
+  }
   if (e != cudaSuccess) return e;
-  if (b.p) { cudaStreamSynchronize(ln->st); cudaFree(b.p); add_bytes(ln->ctx, -(long long)b.cap); }
+  if (b.p) defer_free(ln->ctx, b.p, b.cap);        // kernels already queued on the old buffer stay valid
   b.p = np; b.cap = ncap; add_bytes(ln->ctx, (long long)ncap);
   return cudaSuccess;
 }
@@ -228,8 +250,8 @@ static void release(kmx_ctx* ctx, DBuf& b) { if (b.p) { cudaFree(b.p); add_bytes
 static cudaError_t ensure_pin(Lane* ln, size_t bytes)
 {
   if (bytes <= ln->h_pin_cap) return cudaSuccess;
-  if (ln->h_pin) { cudaStreamSynchronize(ln->st); cudaFreeHost(ln->h_pin); ln->h_pin = nullptr; ln->h_pin_cap = 0; }
-  size_t cap = std::max(bytes, (size_t)1 << 16);
+  if (ln->h_pin) { std::lock_guard<std::mutex> g(ln->ctx->grave_mu); ln->ctx->grave_host.push_back(ln->h_pin); ln->h_pin = nullptr; ln->h_pin_cap = 0; }
+  size_t cap = std::max(bytes + bytes / 2, (size_t)1 << 20);
   cudaError_t e = cudaMallocHost((void**)&ln->h_pin, cap);
   if (e == cudaSuccess) ln->h_pin_cap = cap;
   return e;
@@ -290,7 +312,7 @@ static int lane_create(kmx_ctx* ctx, int id)
   CK(cudaMalloc(&ln->d_boff, P * 8)); CK(cudaMalloc(&ln->d_bcap, P * 4));
   CK(cudaMalloc(&ln->d_cursor, P * 4)); CK(cudaMalloc(&ln->d_kcnt, P * 8));
   ln->h_boff.assign(P, 0); ln->h_bcap.assign(P, 0); ln->h_cursor.assign(P, 0); ln->h_kcnt.assign(P, 0);
-  CK(ensure_pin(ln, (size_t)P * 32 + 256));
+  CK(ensure_pin(ln, (size_t)P * 1024 + ((size_t)1 << 20)));      // big enough for every later use at this P: no pinned reallocation mid-run
   return KMX_OK;
 }
 static void lane_destroy(Lane* ln)
@@ -360,6 +382,7 @@ extern "C" void kmx_destroy(kmx_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto& lp : ctx->lanes) if (lp->st) cudaStreamSynchronize(lp->st);
+  reap(ctx);
   dist_destroy(ctx);
   for (auto& lp : ctx->lanes) lane_destroy(lp.get());
   DBuf* bufs[] = {&ctx->d_lists, &ctx->d_soft, &ctx->solid_in, &ctx->body, &ctx->body2, &ctx->stats, &ctx->keep, &ctx->out_row,
@@ -388,6 +411,7 @@ extern "C" int kmx_sync(kmx_ctx* ctx)
 {
   if (!ctx) return KMX_ERR_ARG;
   for (auto& lp : ctx->lanes) { Lane* ln = lp.get(); CK(cudaStreamSynchronize(ln->st)); }
+  reap(ctx);                                      // nothing of this context is in flight now
   return KMX_OK;
 }
 
@@ -445,8 +469,8 @@ static int grow_buckets(Lane* ln, const std::vector<u64>& need)
     for (u32 p = 0; p < P; p++) if (ln->h_cursor[p])
       CK(cudaMemcpyAsync((char*)nb.p + nboff[p] * rec, (char*)ln->records.p + ln->h_boff[p] * rec,
                          (size_t)std::min<u64>(ln->h_cursor[p], ln->h_bcap[p]) * rec, cudaMemcpyDeviceToDevice, ln->st));
-    CK(cudaStreamSynchronize(ln->st));
-    release(ctx, ln->records);
+    defer_free(ctx, ln->records.p, ln->records.cap);      // the copies above read it; freed when nothing is in flight
+    ln->records.p = nullptr; ln->records.cap = 0;
   }
   ln->records = nb; ln->h_boff = nboff; ln->h_bcap = ncap;
   return KMX_OK;
@@ -465,7 +489,7 @@ static int layout_buckets(Lane* ln, const std::vector<u64>& need)
     ln->h_boff[p] = tot; ln->h_bcap[p] = (u32)c; tot += c;
   }
   if (tot * rec + 256 > ln->records.cap) {
-    if (ln->records.p) { CK(cudaStreamSynchronize(ln->st)); release(ctx, ln->records); }
+    if (ln->records.p) { defer_free(ctx, ln->records.p, ln->records.cap); ln->records.p = nullptr; ln->records.cap = 0; }
     const size_t cap = (size_t)((double)(tot * rec) * 1.1) + 256;
     cudaError_t e = cudaMalloc(&ln->records.p, cap);
     if (e != cudaSuccess) { ln->records.p = nullptr; return fail(ln, KMX_ERR_NOMEM, "bucket slab of %zu bytes: %s", cap, cudaGetErrorString(e)); }
@@ -819,7 +843,7 @@ static int count_hash_binned(Lane* ln, uint32_t sample, uint32_t hard_min, const
     if (tiles >= 0x7FFFFFF0ULL) return KMX_BIN_FALLBACK;
     u_tpref[P] = (u32)tiles;
     if (win_part) memcpy(u_wpart, win_part, (size_t)P * 4);
-    CK(ensure(ln, ln->binbuf, ent * 2 + 256));
+    CK(ensure(ln, ln->binbuf, (size_t)((double)ent * 2.2) + 256));   // 10 % head-room: the next samples differ by a few per cent, no regrowth
     // device meta: [status u64[items] | bin_cursor u32[items] | tickets u32[2]] zeroed per sample; layout upload; results
     const size_t zbytes = (items * 12 + 8 + 15) & ~(size_t)15;
     CK(ensure(ln, ln->binmeta, zbytes + up_bytes + (size_t)P * 8 + 64));
@@ -950,6 +974,7 @@ extern "C" int kmx_run_samples(kmx_ctx* ctx, uint32_t n, const char* const* text
     for (auto& x : th) x.join();
   }
   ctx->active_lanes = 1;
+  reap(ctx);                                      // every lane synchronised its stream before its thread ended
   return first_err.load();
 }
 

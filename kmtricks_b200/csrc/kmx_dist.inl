@@ -136,7 +136,7 @@ static int dist_batch(Lane* ln, u32 lane_idx, u32 i_local, u32 n_local, const ch
   const u32 myf = part_first(P, G, me), myl = part_first(P, G, me + 1);
   std::vector<u64> roff(G + 1, 0);
   for (int g = 0; g < G; g++) { const u64* mg = &meta[(size_t)g * ML]; roff[g + 1] = roff[g] + (mg[myl] - mg[myf]); }
-  CK(ensure(ln, d->recv[lane_idx], roff[G] * rec + 256));
+  CK(ensure(ln, d->recv[lane_idx], (size_t)((double)(roff[G] * rec) * 1.1) + 256));
   char* rbuf = (char*)d->recv[lane_idx].p;
   const u64* mm = &meta[(size_t)me * ML];
   {
@@ -256,6 +256,7 @@ extern "C" int kmx_dist_run_batch(kmx_ctx* ctx, uint32_t n_batch, const char* co
     for (u32 t = 0; t < nlanes; t++) th.emplace_back(work, t);
     for (auto& x : th) x.join();
   }
+  if (!first_err.load()) reap(ctx);               // every lane synchronised its stream: none of this rank's kernels is in flight
   return first_err.load();
 }
 

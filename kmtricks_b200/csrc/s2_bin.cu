@@ -29,6 +29,9 @@
 #include "kmx_internal.h"
 #include "records.cuh"
 
+#include <algorithm>
+#include <mutex>
+
 namespace kmx {
 
 static constexpr int HB_THREADS = 256;
@@ -468,16 +471,20 @@ cudaError_t launch_hash_binned(const HashBinArgs& a, u32 total_tiles, int phase,
     const u64 items = (u64)a.nwin * a.NB;
     if (!items || items >= 0x7FFFFFF0ULL) return items ? cudaErrorInvalidValue : cudaSuccess;
     const size_t smem = (size_t)HC2_WORDS_P * 4;
-    cudaError_t e;
-    if (h16) {
-      e = cudaFuncSetAttribute(hash_bincount_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      hash_bincount_kernel<true><<<(unsigned)items, HC2_THREADS, smem, st>>>(a);
-    } else {
-      e = cudaFuncSetAttribute(hash_bincount_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      hash_bincount_kernel<false><<<(unsigned)items, HC2_THREADS, smem, st>>>(a);
+    // the attribute is set once per device and process (not per launch: several lanes launch concurrently)
+    static std::mutex attr_mu; static bool attr_done[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> g(attr_mu);
+      if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(hash_bincount_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_bincount_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+      }
     }
+    if (h16) hash_bincount_kernel<true><<<(unsigned)items, HC2_THREADS, smem, st>>>(a);
+    else hash_bincount_kernel<false><<<(unsigned)items, HC2_THREADS, smem, st>>>(a);
     *launches += 1;
   }
   return cudaGetLastError();

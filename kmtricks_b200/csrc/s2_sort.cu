@@ -279,8 +279,17 @@ cudaError_t segmented_radix_sort(u32 nseg, const u64* h_seg_off, const u64* h_se
   u64 total = 0;
   for (u32 s = 0; s < nseg; s++) total += (h_seg_end ? h_seg_end[s] : h_seg_off[s + 1]) - h_seg_off[s];
   if (total >= 0xFFFFFFFFULL) return cudaErrorInvalidValue;
+  // pinned staging of the tile table, per host thread.  It only grows, with head-room, and an outgrown buffer is NOT freed here:
+  // cudaFreeHost waits for the whole device, and another lane's NCCL kernel may be waiting for a peer at that moment (see
+  // kmx_api.cu: defer_free); the few hundred KB are kept until the process ends.
   static thread_local RsTile* h_tiles = nullptr; static thread_local u64 h_cap = 0;
-  if (h_cap < nt) { if (h_tiles) cudaFreeHost(h_tiles); cudaError_t e = cudaMallocHost((void**)&h_tiles, nt * sizeof(RsTile)); if (e != cudaSuccess) { h_tiles = nullptr; h_cap = 0; return e; } h_cap = nt; }
+  if (h_cap < nt) {
+    const u64 ncap = std::max<u64>(2 * nt, 2048);
+    RsTile* np = nullptr;
+    cudaError_t e = cudaMallocHost((void**)&np, ncap * sizeof(RsTile));
+    if (e != cudaSuccess) return e;
+    h_tiles = np; h_cap = ncap;
+  }
   u64 ti = 0, before = 0;
   for (u32 s = 0; s < nseg; s++) {
     u64 b = h_seg_off[s], e = h_seg_end ? h_seg_end[s] : h_seg_off[s + 1];

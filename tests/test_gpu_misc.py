@@ -138,3 +138,20 @@ def test_transpose_of_a_window_beyond_65535_row_blocks():
         assert np.array_equal(back, a)
     finally:
         eng.close()
+
+
+def test_buffers_that_grow_from_sample_to_sample_over_several_lanes():
+    """Samples of growing size over three lanes: every per-lane buffer (bucket slab, bin buffer, text staging, ...) is outgrown
+    several times while other lanes are in flight.  Outgrown buffers are set aside, not freed on the spot (a cudaFree waits for
+    the whole device; with NCCL kernels of other lanes in flight that wait closed a cycle over lanes and ranks at 8 GPUs); the
+    results stay those of the oracle and the memory comes back at the next synchronisation point."""
+    from kmtricks_b200 import engine, synth
+    from oracle import oracle as O
+    texts = [synth.make_fastq(3, s, 2000 * (s + 1), L=150, G=50000, d=4e-3, e=4e-3, revcomp=True) for s in range(7)]
+    for mode, extra in (("hash:bf:bin", dict(bloom_size=400_000)), ("kmer:count:bin", {})):
+        cfg = engine.Config(kmer_size=31, nb_partitions=8, mode=mode, hard_min=2, **extra)
+        got = engine.run_pipeline_lanes(texts, cfg, lanes=3)
+        want = O.run_pipeline([[t] for t in texts], O.Params(k=31, P=8, mode=mode, hard_min=2, **extra))
+        for p in range(8):
+            assert got["matrices"][p] == want["matrices"][p], f"{mode}: matrix {p}"
+            assert got["merge_info"][p] == want["merge_info"][p]

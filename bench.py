@@ -29,7 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # several lanes = several streams and NCCL communicators per GPU: give every stream its own hardware queue, so that a
 # collective kernel waiting for its peers never sits in front of another lane's kernel (must be set before CUDA starts)
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 # survey §8(d) "Algorithmic bytes": S1 = read FASTQ + write buckets at the reference's compact
 # super-k-mer format (1.03 B per k-mer, measured on the reference's skp files)

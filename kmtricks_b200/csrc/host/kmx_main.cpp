@@ -573,7 +573,8 @@ void merge_partitions(Run& R, const Rank& rk, PluginHost& plug, const std::vecto
 int main(int argc, char** argv)
 {
   const auto t0 = std::chrono::steady_clock::now();
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);        // one hardware queue per stream: lanes (and their NCCL kernels) never queue behind each other
+  for (int i = 1; i < argc; i++) if (std::string(argv[i]) == "--devices")
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);      // multi-GPU: one hardware queue per stream, so a lane's NCCL kernel never sits in front of another lane's
   std::vector<Rank> ranks;
   try {
     if (argc == 3 && std::string(argv[1]) == "fof") {     // host-side check, no device: prints the parsed input list

@@ -43,6 +43,7 @@ static const char* nccl_load()
 struct KmxDist {
   int rank = 0, world = 1;
   u32 use_lanes = 0;                      // 0 = all
+  u32 warmed_lanes = 0;                   // lanes whose first sample has been through alone (see kmx_dist_run_batch)
   std::vector<ncclComm_t> comms;          // one per lane
   std::vector<DBuf> recv, meta_dev;       // per lane
 };
@@ -238,12 +239,29 @@ extern "C" int kmx_dist_run_batch(kmx_ctx* ctx, uint32_t n_batch, const char* co
     }
   }
   ctx->active_lanes = (int)nlanes;
+  // First call of a context: the first sample of every lane goes through ALONE, one lane after the other, on every rank alike.
+  // That is where each lane's buffers are allocated (and outgrown the first few times); allocations and frees are device-wide
+  // synchronisation points, and taken while another lane's NCCL kernel waits for a peer they can close a cycle over lanes and
+  // ranks (the first step hung at 8 GPUs).  Afterwards the lanes run concurrently and nothing is allocated in the steady state.
+  u32 start = 0;
+  if (d->warmed_lanes < nlanes) {
+    const u32 npro = std::min<u32>(nlanes, n_batch);
+    cudaSetDevice(ctx->device);
+    for (u32 i = 0; i < npro; i++) {
+      Lane* ln = ctx->lanes[i].get();
+      int rc = dist_batch(ln, i, slot_base + i, n_local, texts[i], nbytes[i], on_device, hard_min[i],
+                          kmers_per_partition ? kmers_per_partition + (size_t)i * P : nullptr);
+      if (!rc && cudaStreamSynchronize(ln->st) != cudaSuccess) rc = fail(ln, KMX_ERR_CUDA, "stream synchronisation failed");
+      if (rc) return rc;
+    }
+    d->warmed_lanes = std::max(d->warmed_lanes, npro); start = npro;
+  }
   std::atomic<int> first_err(0);
   auto work = [&](u32 t) {
     cudaSetDevice(ctx->device);
     Lane* ln = ctx->lanes[t].get();
     // every rank walks the same (lane, sample) schedule, so the collectives of a lane's communicator match up
-    for (u32 i = t; i < n_batch; i += nlanes) {
+    for (u32 i = start + t; i < n_batch; i += nlanes) {
       int rc = first_err.load() ? first_err.load() : dist_batch(ln, t, slot_base + i, n_local, texts[i], nbytes[i], on_device, hard_min[i],
                                                                 kmers_per_partition ? kmers_per_partition + (size_t)i * P : nullptr);
       if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); return; }
